@@ -379,7 +379,7 @@ struct Oracle {
     int nlights = 0;
     // light/world.py:10-16
     V4 world_fac{0.1f, 0.1f, 0.1f, 0.1f};
-    int world_tex = -1;
+    int world_tex = 0;   // zero-initialised field (world.py:12)
     // camera.py:10-12
     float V2W[4][4];
     // filmtable.py:12-14
@@ -679,6 +679,7 @@ struct Oracle {
 
     // ---- image.py:21-24,137-148, common.py:183-192 -----------------------------------------
     inline V4 img_fetch(int id, int x, int y) const {
+        if (img_nx[id] <= 0 || img_ny[id] <= 0) return V4{0, 0, 0, 0};  // unloaded image: `x % 0` in the reference (UB); fenced
         x = pymod(x, img_nx[id]); y = pymod(y, img_ny[id]);
         return texels[(size_t)img_base[id] + (size_t)x * img_ny[id] + y];
     }

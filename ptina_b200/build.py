@@ -1,0 +1,64 @@
+"""Builds libptina_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(HERE, 'libptina_b200.so')
+SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu']
+HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', '../../include/ptina_b200.h']
+
+# -fmad=false / -prec-div / -prec-sqrt / -ftz=false: IEEE binary32 in source order -- what makes Morton codes, primary
+# rays and the box/triangle predicates bit-identical to a strict CPU evaluation (DESIGN.md "Arithmetic contract").
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', shutil.which('nvcc')):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found (needed to build libptina_b200.so)')
+
+
+def stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(f) > t for f in files)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return SO
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    if os.path.exists('/usr/bin/g++'):
+        ccbin = ['-ccbin', '/usr/bin/g++']
+    else:
+        ccbin = []
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
+    cmd = [nvcc] + ccbin + ['-shared', '-o', SO] + objs + ['-lcudart']
+    subprocess.check_call(cmd, env=env)
+    return SO
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

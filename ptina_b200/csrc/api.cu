@@ -1,0 +1,432 @@
+// api.cu -- the C ABI of include/ptina_b200.h: context, loaders, film, render entry points, parity taps.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "ptb_internal.h"
+
+static thread_local char g_err[512] = "";
+void ptb_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+TraceScene ptb_trace_scene(const ptb_ctx* c) {
+    TraceScene S;
+    S.nodes = c->d_nodes; S.tris = c->d_tris; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
+    for (int k = 0; k < 3; k++) { S.root_lo[k] = c->root_lo[k]; S.root_hi[k] = c->root_hi[k]; }
+    return S;
+}
+int ptb_effective_policy(const ptb_ctx* c, int requested) {
+    if (requested == PTB_TRAVERSE_REFERENCE) return PTB_TRAVERSE_REFERENCE;
+    bool ok = c->tree_info.valid && c->tree_info.depth <= PTB_STACK;
+    return ok ? PTB_TRAVERSE_ORDERED : PTB_TRAVERSE_REFERENCE;   // AUTO and ORDERED both need a proper tree
+}
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+template <class T> int dmalloc(T** p, size_t count) {
+    PTB_CUDA(cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+// stage a host array on the device (or pass a device pointer through)
+template <class T> struct In {
+    const T* dev = nullptr; T* owned = nullptr;
+    int set(ptb_ctx* c, const T* src, size_t count, int memspace = PTB_HOST) {
+        if (!src) return 0;
+        if (memspace == PTB_DEVICE) { dev = src; return 0; }
+        PTB_CUDA(cudaMalloc((void**)&owned, sizeof(T) * (count ? count : 1)));
+        PTB_CUDA(cudaMemcpyAsync(owned, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+        dev = owned;
+        return 0;
+    }
+    ~In() { if (owned) cudaFree(owned); }
+};
+template <class T> struct Out {
+    T* dev = nullptr; T* host = nullptr; size_t count = 0; bool owned = false;
+    int set(T* dst, size_t n, int memspace = PTB_HOST) {
+        if (!dst) return 0;
+        count = n;
+        if (memspace == PTB_DEVICE) { dev = dst; return 0; }
+        host = dst; owned = true;
+        PTB_CUDA(cudaMalloc((void**)&dev, sizeof(T) * (n ? n : 1)));
+        return 0;
+    }
+    int finish(ptb_ctx* c) {
+        if (host) {
+            PTB_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, c->stream));
+            PTB_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return 0;
+    }
+    ~Out() { if (owned && dev) cudaFree(dev); }
+};
+}  // namespace
+
+#define CHECK_CTX(c) do { if (!(c)) { ptb_set_error("null context"); return 1; } } while (0)
+
+extern "C" {
+
+const char* ptb_last_error(void) { return g_err; }
+int ptb_version(void) { return 100; }
+
+int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        ptb_set_error("no CUDA device: %s (ptina_b200 has no CPU fallback)", cudaGetErrorString(e));
+        return 1;
+    }
+    if (device < 0 || device >= ndev) { ptb_set_error("device %d out of range (%d visible)", device, ndev); return 1; }
+    PTB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { ptb_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return 1; }
+    ptb_ctx* c = new ptb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ptb_caps d{};
+    if (caps) d = *caps;
+    if (d.max_faces <= 0) d.max_faces = 1 << 21;          // things.py:13
+    if (d.max_texels <= 0) d.max_texels = 1 << 22;        // things.py:14
+    if (d.max_materials <= 0) d.max_materials = 64;
+    if (d.max_textures <= 0) d.max_textures = 64;
+    if (d.max_lights <= 0) d.max_lights = 64;
+    if (d.max_filmsize <= 0) d.max_filmsize = 1 << 21;    // things.py:18
+    if (d.max_filmpasses <= 0) d.max_filmpasses = 3;
+    if (d.max_paths <= 0) d.max_paths = 1 << 23;
+    if (d.max_materials > PTB_MAX_MATERIALS || d.max_textures > PTB_MAX_TEXTURES || d.max_lights > PTB_MAX_LIGHTS || d.max_filmpasses < 3) {
+        ptb_set_error("capacities beyond the compiled table sizes (64 materials / textures / lights, >= 3 film passes)");
+        delete c; return 1;
+    }
+    c->caps = d;
+    c->max_paths = d.max_paths;
+    size_t nf = (size_t)d.max_faces;
+    if (dmalloc(&c->d_verts, nf * 24) || dmalloc(&c->d_mtlids, nf) || dmalloc(&c->d_texels, (size_t)d.max_texels) ||
+        dmalloc(&c->d_mc, nf) || dmalloc(&c->d_id, nf) || dmalloc(&c->d_mc_tmp, nf) || dmalloc(&c->d_id_tmp, nf) || dmalloc(&c->d_leaf, nf) ||
+        dmalloc(&c->d_child, nf) || dmalloc(&c->d_bmin, nf * 3) || dmalloc(&c->d_bmax, nf * 3) || dmalloc(&c->d_ready, nf) ||
+        dmalloc(&c->d_parentcnt, nf * 2) || dmalloc(&c->d_range, nf) || dmalloc(&c->d_height, nf) || dmalloc(&c->d_nodes, nf) ||
+        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
+        delete c; return 1;
+    }
+    PTB_CUDA(cudaMemset(c->d_film, 0, sizeof(float4) * (size_t)d.max_filmsize * d.max_filmpasses));
+    PTB_CUDA(cudaMemset(c->d_texels, 0, sizeof(float4) * (size_t)d.max_texels));
+    if (ptb_wf_init(c)) { delete c; return 1; }
+    // defaults of the reference singletons
+    memset(&c->h_params, 0, sizeof c->h_params);
+    for (int k = 0; k < 4; k++) c->h_params.world_fac[k] = 0.1f;       // light/world.py:14-16 (tex field zero-initialised)
+    c->h_params.world_tex = 0;
+    LightRec& L = c->h_params.lights[0];                                // light/__init__.py:22-28 default light
+    L.type = PTB_LIGHT_POINT; L.size = 0.5f; L.color = mk3(32.f, 32.f, 32.f); L.pos = mk3(1.f, 2.f, 3.f);
+    c->h_params.nlights = 1;
+    c->params_dirty = true;
+    *out = c;
+    return 0;
+}
+
+int ptb_destroy(ptb_ctx* c) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_sort_tmp, c->d_scalars,
+                    c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->st.sh_d, c->st.sh_c, c->d_queue[0], c->d_queue[1], c->d_shadowq,
+                    c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    delete c;
+    return 0;
+}
+
+int ptb_set_stream(ptb_ctx* c, void* s) { CHECK_CTX(c); c->stream = (cudaStream_t)s; return 0; }
+int ptb_synchronize(ptb_ctx* c) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    return ptb_stage_collect(c);
+}
+
+// ---- Sobol ------------------------------------------------------------------------------------------------------
+int ptb_set_sobol_table(ptb_ctx* c, const int32_t* V, int rows, int dim) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (rows != PTB_SOBOL_ROWS || dim <= 0) { ptb_set_error("Sobol table must be [21][dim]"); return 1; }
+    if (c->d_sobolV) cudaFree(c->d_sobolV);
+    PTB_CUDA(cudaMalloc(&c->d_sobolV, sizeof(int32_t) * rows * dim));
+    PTB_CUDA(cudaMemcpy(c->d_sobolV, V, sizeof(int32_t) * rows * dim, cudaMemcpyHostToDevice));
+    c->sobol_dim = dim;
+    if (c->d_sobolP) { cudaFree(c->d_sobolP); c->d_sobolP = nullptr; c->sobolP_cap = 0; }
+    c->sobol_time = 64;     // reset(): time = 0 then skip = 64 updates (sobol.py:75, 92-97)
+    return 0;
+}
+int ptb_sobol_reset(ptb_ctx* c) { CHECK_CTX(c); c->sobol_time = 64; return 0; }
+int ptb_sobol_get_time(ptb_ctx* c, int* t) { CHECK_CTX(c); *t = c->sobol_time; return 0; }
+int ptb_sobol_set_time(ptb_ctx* c, int t) { CHECK_CTX(c); c->sobol_time = t; return 0; }
+int ptb_sobol_point(ptb_ctx* c, int k, float* P_out) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    Out<float> o;
+    if (o.set(P_out, c->sobol_dim)) return 1;
+    if (ptb_wf_sobol_points(c, k, 1, 1, o.dev)) return 1;
+    return o.finish(c);
+}
+
+// ---- loaders ------------------------------------------------------------------------------------------------------
+int ptb_load_model(ptb_ctx* c, const float* verts, const int32_t* mtlids, int nfaces, int memspace) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (nfaces < 0 || !(nfaces < c->caps.max_faces)) { ptb_set_error("too many faces"); return 1; }   // model.py:84
+    cudaMemcpyKind kind = memspace == PTB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (nfaces) {
+        PTB_CUDA(cudaMemcpyAsync(c->d_verts, verts, sizeof(float) * 24 * (size_t)nfaces, kind, c->stream));
+        PTB_CUDA(cudaMemcpyAsync(c->d_mtlids, mtlids, sizeof(int32_t) * (size_t)nfaces, kind, c->stream));
+    }
+    c->nfaces = nfaces;
+    c->tree_n = -1;   // stale until build_tree
+    return 0;
+}
+int ptb_load_materials(ptb_ctx* c, const float* fac, const int32_t* tex, int nmat) {
+    CHECK_CTX(c);
+    if (nmat < 0 || nmat > c->caps.max_materials) { ptb_set_error("too many materials (%d > %d)", nmat, c->caps.max_materials); return 1; }
+    memcpy(c->h_params.mat_fac, fac, sizeof(float) * 48 * nmat);
+    memcpy(c->h_params.mat_tex, tex, sizeof(int32_t) * 12 * nmat);
+    c->params_dirty = true;
+    return 0;
+}
+int ptb_load_images(ptb_ctx* c, const float* texels, int64_t ntexels, const int32_t* nx, const int32_t* ny, const int32_t* base, int nimg, int memspace) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (nimg > c->caps.max_textures) { ptb_set_error("Out of ID!"); return 1; }          // allocator.py:53
+    if (ntexels > c->caps.max_texels) { ptb_set_error("Out of memory!"); return 1; }     // allocator.py:25
+    for (int i = 0; i < nimg; i++) {
+        if (nx[i] <= 0 || ny[i] <= 0 || base[i] < 0 || (int64_t)base[i] + (int64_t)nx[i] * ny[i] > ntexels) { ptb_set_error("image %d outside the texel arena", i); return 1; }
+        c->h_params.img_nx[i] = nx[i]; c->h_params.img_ny[i] = ny[i]; c->h_params.img_base[i] = base[i];
+    }
+    if (ntexels) PTB_CUDA(cudaMemcpyAsync(c->d_texels, texels, sizeof(float4) * (size_t)ntexels, memspace == PTB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    c->params_dirty = true;
+    return 0;
+}
+int ptb_clear_lights(ptb_ctx* c) { CHECK_CTX(c); c->h_params.nlights = 0; c->params_dirty = true; return 0; }
+int ptb_add_light(ptb_ctx* c, const float pos[3], const float axes[9], const float color[3], float size, int type) {
+    CHECK_CTX(c);
+    int i = c->h_params.nlights;
+    if (i >= c->caps.max_lights) { ptb_set_error("too many lights"); return 1; }
+    if (type != PTB_LIGHT_POINT && type != PTB_LIGHT_AREA) { ptb_set_error("unknown light type %d", type); return 1; }
+    LightRec& L = c->h_params.lights[i];
+    L.type = type; L.size = size;
+    L.color = mk3(color[0], color[1], color[2]); L.pos = mk3(pos[0], pos[1], pos[2]);
+    for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) L.axes.m[r][k] = axes[3 * r + k];
+    c->h_params.nlights = i + 1;
+    c->params_dirty = true;
+    return 0;
+}
+int ptb_set_world_light(ptb_ctx* c, const float fac[4], int tex) {
+    CHECK_CTX(c);
+    for (int k = 0; k < 4; k++) c->h_params.world_fac[k] = fac[k];
+    c->h_params.world_tex = tex;
+    c->params_dirty = true;
+    return 0;
+}
+int ptb_set_camera(ptb_ctx* c, const float v2w[16], const float w2v[16]) {
+    CHECK_CTX(c);
+    memcpy(c->h_params.v2w, v2w, 64);
+    if (w2v) memcpy(c->h_w2v, w2v, 64);
+    c->params_dirty = true;
+    return 0;
+}
+
+// ---- tree ------------------------------------------------------------------------------------------------------------
+int ptb_build_tree(ptb_ctx* c, ptb_tree_info* info) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    int rc = ptb_lbvh_build(c);
+    if (info) *info = c->tree_info;
+    return rc;
+}
+int ptb_set_traversal(ptb_ctx* c, int policy) {
+    CHECK_CTX(c);
+    if (policy < 0 || policy > 2) { ptb_set_error("unknown traversal policy %d", policy); return 1; }
+    c->traversal_request = policy;
+    c->tree_info.policy = ptb_effective_policy(c, policy);
+    return 0;
+}
+int ptb_export_tree(ptb_ctx* c, int32_t* mc, int32_t* id, int32_t* child, int32_t* leaf, float* bmin, float* bmax) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    int n = c->tree_n;
+    if (n < 0) { ptb_set_error("no tree built"); return 1; }
+    cudaStream_t s = c->stream;
+    if (mc && n) PTB_CUDA(cudaMemcpyAsync(mc, c->d_mc, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (id && n) PTB_CUDA(cudaMemcpyAsync(id, c->d_id, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (leaf && n) PTB_CUDA(cudaMemcpyAsync(leaf, c->d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (n > 1) {
+        if (child) PTB_CUDA(cudaMemcpyAsync(child, c->d_child, 8 * (size_t)(n - 1), cudaMemcpyDeviceToHost, s));
+        if (bmin) PTB_CUDA(cudaMemcpyAsync(bmin, c->d_bmin, 12 * (size_t)(n - 1), cudaMemcpyDeviceToHost, s));
+        if (bmax) PTB_CUDA(cudaMemcpyAsync(bmax, c->d_bmax, 12 * (size_t)(n - 1), cudaMemcpyDeviceToHost, s));
+    }
+    PTB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---- film ------------------------------------------------------------------------------------------------------------
+int ptb_set_size(ptb_ctx* c, int nx, int ny) {
+    CHECK_CTX(c);
+    if (nx <= 0 || ny <= 0 || (int64_t)nx * ny > c->caps.max_filmsize) { ptb_set_error("film %dx%d exceeds max_filmsize %d", nx, ny, c->caps.max_filmsize); return 1; }
+    c->nx = nx; c->ny = ny;
+    c->params_dirty = true;
+    return 0;
+}
+int ptb_get_size(ptb_ctx* c, int* nx, int* ny) { CHECK_CTX(c); *nx = c->nx; *ny = c->ny; return 0; }
+int ptb_clear(ptb_ctx* c) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    PTB_CUDA(cudaMemsetAsync(c->d_film, 0, sizeof(float4) * (size_t)c->caps.max_filmsize * c->caps.max_filmpasses, c->stream));
+    return 0;
+}
+int ptb_film_ptr(ptb_ctx* c, int pass, void** dev_ptr, int64_t* ntexels) {
+    CHECK_CTX(c);
+    if (pass < 0 || pass >= c->caps.max_filmpasses) { ptb_set_error("film pass %d out of range", pass); return 1; }
+    *dev_ptr = c->d_film + (size_t)pass * c->caps.max_filmsize;
+    if (ntexels) *ntexels = (int64_t)c->nx * c->ny;
+    return 0;
+}
+
+// ---- render ----------------------------------------------------------------------------------------------------------
+int ptb_render(ptb_ctx* c, int engine, int nsamples) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (nsamples <= 0) return 0;
+    if (engine == PTB_ENGINE_MLT) return ptb_wf_render(c, engine, 0, nsamples, 1, nullptr);
+    int k_first = c->sobol_time + 1;          // update() runs before _render (path.py:75-77)
+    int rc = ptb_wf_render(c, engine, k_first, nsamples, 1, nullptr);
+    if (rc == 0) c->sobol_time += nsamples;
+    return rc;
+}
+int ptb_render_range(ptb_ctx* c, int engine, int k_first, int count, int stride) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (count <= 0) return 0;
+    return ptb_wf_render(c, engine, k_first, count, stride, nullptr);
+}
+int ptb_render_sample(ptb_ctx* c, int engine, int k, float* out) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    Out<float> o;
+    if (o.set(out, (size_t)c->nx * c->ny * 3)) return 1;
+    if (ptb_wf_render(c, engine, k, 1, 1, o.dev)) return 1;
+    return o.finish(c);
+}
+int ptb_mlt_reset(ptb_ctx* c, uint64_t seed, int chain_first, int chain_count) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (chain_count <= 0 || chain_count > c->max_paths) { ptb_set_error("chain count %d outside (0, %lld]", chain_count, (long long)c->max_paths); return 1; }
+    if (chain_count != c->mlt_count) {
+        if (c->d_Xold) { cudaFree(c->d_Xold); cudaFree(c->d_Xnew); cudaFree(c->d_Lold); }
+        if (dmalloc(&c->d_Xold, (size_t)chain_count * 32) || dmalloc(&c->d_Xnew, (size_t)chain_count * 32) || dmalloc(&c->d_Lold, (size_t)chain_count)) return 1;
+    }
+    c->mlt_seed = seed; c->mlt_first = chain_first; c->mlt_count = chain_count;
+    return ptb_wf_mlt_reset(c);
+}
+int ptb_mlt_set_param(ptb_ctx* c, float lsp, float sigma) { CHECK_CTX(c); c->mlt_lsp = lsp; c->mlt_sigma = sigma; return 0; }
+
+static int resolve_common(ptb_ctx* c, int pass, int mode, float* out, int memspace, size_t count) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (pass < 0 || pass >= c->caps.max_filmpasses) { ptb_set_error("film pass %d out of range", pass); return 1; }
+    Out<float> o;
+    if (o.set(out, count, memspace)) return 1;
+    if (ptb_wf_resolve(c, pass, mode, o.dev)) return 1;
+    return o.finish(c);
+}
+int ptb_get_image(ptb_ctx* c, int pass, float* out, int memspace) { return resolve_common(c, pass, 0, out, memspace, c ? (size_t)c->nx * c->ny * 4 : 0); }
+int ptb_fast_export_image(ptb_ctx* c, int pass, float* out, int memspace) { return resolve_common(c, pass, 1, out, memspace, c ? (size_t)c->nx * c->ny * 3 : 0); }
+int ptb_get_film(ptb_ctx* c, int pass, float* out, int memspace) { return resolve_common(c, pass, 2, out, memspace, c ? (size_t)c->nx * c->ny * 4 : 0); }
+
+// ---- taps ------------------------------------------------------------------------------------------------------------
+int ptb_trace_primary(ptb_ctx* c, int k, float* rays, int32_t* hit, float* depth, int32_t* index, float* uv) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    size_t np = (size_t)c->nx * c->ny;
+    Out<float> o_rays, o_depth, o_uv; Out<int32_t> o_hit, o_index;
+    if (o_rays.set(rays, np * 6) || o_depth.set(depth, np) || o_uv.set(uv, np * 2) || o_hit.set(hit, np) || o_index.set(index, np)) return 1;
+    if (ptb_wf_trace_primary(c, k, o_rays.dev, o_hit.dev, o_depth.dev, o_index.dev, o_uv.dev)) return 1;
+    return o_rays.finish(c) || o_depth.finish(c) || o_uv.finish(c) || o_hit.finish(c) || o_index.finish(c);
+}
+int ptb_intersect(ptb_ctx* c, const float* rays, const int32_t* avoid, int m, int policy, int32_t* hit, float* depth, int32_t* index, float* uv) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (m <= 0) return 0;
+    In<float> i_rays; In<int32_t> i_avoid;
+    Out<float> o_depth, o_uv; Out<int32_t> o_hit, o_index;
+    if (i_rays.set(c, rays, (size_t)m * 6) || i_avoid.set(c, avoid, m)) return 1;
+    if (o_hit.set(hit, m) || o_depth.set(depth, m) || o_index.set(index, m) || o_uv.set(uv, (size_t)m * 2)) return 1;
+    if (!o_hit.dev || !o_depth.dev || !o_index.dev || !o_uv.dev) { ptb_set_error("ptb_intersect needs all four outputs"); return 1; }
+    if (ptb_wf_intersect(c, i_rays.dev, i_avoid.dev, nullptr, m, policy, 0, o_hit.dev, o_depth.dev, o_index.dev, o_uv.dev)) return 1;
+    return o_hit.finish(c) || o_depth.finish(c) || o_index.finish(c) || o_uv.finish(c);
+}
+int ptb_occluded(ptb_ctx* c, const float* rays, const int32_t* avoid, const float* dis, int m, int policy, int32_t* occluded) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (m <= 0) return 0;
+    In<float> i_rays, i_dis; In<int32_t> i_avoid; Out<int32_t> o;
+    if (i_rays.set(c, rays, (size_t)m * 6) || i_dis.set(c, dis, m) || i_avoid.set(c, avoid, m) || o.set(occluded, m)) return 1;
+    if (ptb_wf_intersect(c, i_rays.dev, i_avoid.dev, i_dis.dev, m, policy, 1, o.dev, nullptr, nullptr, nullptr)) return 1;
+    return o.finish(c);
+}
+static int shade_tap(ptb_ctx* c, int what, const float* in0, size_t n0, const float* in1, size_t n1, const int32_t* ini, int m, float* out, size_t nout) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (m <= 0) return 0;
+    In<float> a, b; In<int32_t> ii; Out<float> o;
+    if (a.set(c, in0, n0) || b.set(c, in1, n1) || ii.set(c, ini, m) || o.set(out, nout)) return 1;
+    if (ptb_wf_shade_tap(c, what, a.dev, b.dev, ii.dev, m, o.dev)) return 1;
+    return o.finish(c);
+}
+int ptb_eval_bsdf(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 0, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 3); }
+int ptb_sample_bsdf(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 1, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 7); }
+int ptb_material_get(ptb_ctx* c, const int32_t* mtlid, const float* uv, int m, float* out) { return shade_tap(c, 2, uv, (size_t)m * 2, nullptr, 0, mtlid, m, out, (size_t)m * 14); }
+int ptb_light_hit(ptb_ctx* c, const float* rays, int m, float* out) { return shade_tap(c, 3, rays, (size_t)m * 6, nullptr, 0, nullptr, m, out, (size_t)m * 6); }
+int ptb_light_sample(ptb_ctx* c, const float* in, int m, float* out) { return shade_tap(c, 4, in, (size_t)m * 6, nullptr, 0, nullptr, m, out, (size_t)m * 8); }
+int ptb_world_at(ptb_ctx* c, const float* dirs, int m, float* out) { return shade_tap(c, 5, dirs, (size_t)m * 3, nullptr, 0, nullptr, m, out, (size_t)m * 3); }
+
+int ptb_set_counting(ptb_ctx* c, int enabled) { CHECK_CTX(c); c->counting = enabled & 1; c->profiling = (enabled >> 1) & 1; return 0; }
+int ptb_get_counters(ptb_ctx* c, ptb_counters* out) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    DevCounters h;
+    PTB_CUDA(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    out->extend_rays = (int64_t)h.extend_rays; out->shadow_rays = (int64_t)h.shadow_rays; out->rays = out->extend_rays + out->shadow_rays;
+    out->node_visits = (int64_t)h.nodes; out->box_tests = (int64_t)h.boxes; out->tri_tests = (int64_t)h.tris; out->paths = (int64_t)h.paths;
+    out->max_stack = h.max_stack;
+    return 0;
+}
+int ptb_reset_counters(ptb_ctx* c) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    PTB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
+    if (ptb_stage_collect(c)) return 1;
+    for (float& f : c->stage_ms) f = 0.0f;
+    c->launches = 0;
+    return 0;
+}
+int ptb_get_stage_ms(ptb_ctx* c, float ms[5]) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    if (ptb_stage_collect(c)) return 1;
+    for (int i = 0; i < 5; i++) ms[i] = c->stage_ms[i];
+    return 0;
+}
+int ptb_get_launches(ptb_ctx* c, int64_t* n) { CHECK_CTX(c); *n = c->launches; return 0; }
+int ptb_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    return ptb_wf_measure_l2(c, mbytes, iters, gbps);
+}
+
+}  // extern "C"

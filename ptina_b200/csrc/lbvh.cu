@@ -1,0 +1,335 @@
+// lbvh.cu -- LBVH build on the device, bit-identical to the reference's tree/lbvh.py:
+//   genMortonCodes (lbvh.py:168-183) -> sortMortonCodes (lbvh.py:186-208; the reference round-trips through the host
+//   and np.argsort -- here cub::DeviceRadixSort, stable, so ties keep face order) -> genHierarchy (lbvh.py:211-231
+//   with determineRange lbvh.py:93-145, findSplit lbvh.py:61-90 and the quirky clz lbvh.py:33-42) ->
+//   genAABBs (lbvh.py:251-294, level-synchronous sweeps; min/max are exact so the boxes are identical).
+// Then: validation (every node one parent, leaf slots in order, height) and packing into the 64-byte node /
+// triangle records the traversal kernels read (ptb_traverse.cuh).
+#include <cub/cub.cuh>
+#include "ptb_internal.h"
+
+namespace {
+
+constexpr int BLK = 256;
+
+__device__ __forceinline__ void atomicMinF(float* a, float v) {
+    if (v >= 0.0f) atomicMin((int*)a, __float_as_int(v)); else atomicMax((unsigned*)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomicMaxF(float* a, float v) {
+    if (v >= 0.0f) atomicMax((int*)a, __float_as_int(v)); else atomicMin((unsigned*)a, __float_as_uint(v));
+}
+
+__device__ __forceinline__ V3 face_vertex(const float* __restrict__ verts, int face, int k) {
+    const float* p = verts + (size_t)(face * 3 + k) * 8;
+    return mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+// lbvh.py:161-165 getCenter
+__device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int face) {
+    return (face_vertex(verts, face, 0) + face_vertex(verts, face, 1) + face_vertex(verts, face, 2)) / 3.0f;
+}
+
+// scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height
+__global__ void k_init_scalars(float* s) {
+    s[0] = s[1] = s[2] = PTB_INF;
+    s[3] = s[4] = s[5] = -PTB_INF;
+    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0;
+}
+
+// lbvh.py:172-176: bounds of the triangle CENTRES (atomic min/max; exact, order-free)
+__global__ void __launch_bounds__(BLK) k_center_bounds(const float* __restrict__ verts, int n, float* s) {
+    V3 lo = v3s(PTB_INF), hi = v3s(-PTB_INF);
+    for (int i = blockIdx.x * BLK + threadIdx.x; i < n; i += gridDim.x * BLK) {
+        V3 c = face_center(verts, i);
+        lo = vmin(lo, c); hi = vmax(hi, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(~0u, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(~0u, lo.y, o)); lo.z = fminf(lo.z, __shfl_xor_sync(~0u, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(~0u, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(~0u, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(~0u, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMinF(&s[0], lo.x); atomicMinF(&s[1], lo.y); atomicMinF(&s[2], lo.z);
+        atomicMaxF(&s[3], hi.x); atomicMaxF(&s[4], hi.y); atomicMaxF(&s[5], hi.z);
+    }
+}
+
+// lbvh.py:12-23 expandBits (wrapping i32 multiply == u32 multiply), lbvh.py:26-30 morton3D
+__device__ __forceinline__ int expand_bits(int v_) {
+    unsigned v = (unsigned)v_;
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return (int)v;
+}
+__device__ __forceinline__ int morton3d(V3 v) {
+    int wx = expand_bits(clampi(ifloor(v.x * 1024.0f), 0, 1023));
+    int wy = expand_bits(clampi(ifloor(v.y * 1024.0f), 0, 1023));
+    int wz = expand_bits(clampi(ifloor(v.z * 1024.0f), 0, 1023));
+    return wx * 4 + wy * 2 + wz;
+}
+// lbvh.py:178-183
+__global__ void __launch_bounds__(BLK) k_morton(const float* __restrict__ verts, int n, const float* __restrict__ s, int* mc, int* id) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n) return;
+    V3 lo = mk3(s[0], s[1], s[2]), hi = mk3(s[3], s[4], s[5]);
+    V3 c = face_center(verts, i);
+    V3 coord = (c - lo) / (hi - lo);
+    mc[i] = morton3d(coord);
+    id[i] = i;
+}
+
+// lbvh.py:33-42: min(clz32(x)+1, 32) -- XOR values 0 and 1 are indistinguishable, as in the reference
+__device__ __forceinline__ int clz_ref(int x) { return min(__clz(x) + 1, 32); }
+
+// lbvh.py:61-90
+__device__ int find_split(const int* __restrict__ mc, int l, int r) {
+    int lc = mc[l], rc = mc[r];
+    if (lc == rc) return (l + r) >> 1;
+    int cp = clz_ref(lc ^ rc);
+    int m = l, s = r - l;
+    while (true) {
+        s += 1; s >>= 1;
+        int nn = m + s;
+        if (nn < r) {
+            int sp = clz_ref(lc ^ mc[nn]);
+            if (sp > cp) m = nn;
+        }
+        if (s <= 1) break;
+    }
+    return m;
+}
+// lbvh.py:93-145
+__device__ void determine_range(const int* __restrict__ mc, int n, int i, int* lo, int* ro) {
+    int l = 0, r = n - 1;
+    if (i != 0) {
+        int ic = mc[i], lc = mc[i - 1], rc = mc[i + 1];
+        if (lc == ic && ic == rc) {
+            l = i;
+            while (i < n - 1) {
+                i += 1;
+                if (i >= n - 1) break;
+                if (mc[i] != mc[i + 1]) break;
+            }
+            r = i;
+        } else {
+            int ld = clz_ref(ic ^ lc), rd = clz_ref(ic ^ rc);
+            int d = rd > ld ? 1 : -1;
+            int delta_min = min(ld, rd);
+            int lmax = 2;
+            int delta = -1;
+            int itmp = i + d * lmax;
+            if (0 <= itmp && itmp < n) delta = clz_ref(ic ^ mc[itmp]);
+            while (delta > delta_min) {
+                lmax <<= 1;
+                itmp = i + d * lmax;
+                delta = -1;
+                if (0 <= itmp && itmp < n) delta = clz_ref(ic ^ mc[itmp]);
+            }
+            int s = 0;
+            for (int t = lmax >> 1; t > 0; t >>= 1) {
+                itmp = i + (s + t) * d;
+                delta = -1;
+                if (0 <= itmp && itmp < n) delta = clz_ref(ic ^ mc[itmp]);
+                if (delta > delta_min) s += t;
+            }
+            l = i; r = i + s * d;
+            if (d < 0) { int t = l; l = r; r = t; }
+        }
+    }
+    *lo = l; *ro = r;
+}
+// lbvh.py:211-231
+__global__ void __launch_bounds__(BLK) k_hierarchy(const int* __restrict__ mc, const int* __restrict__ id, int n, int* leaf, int2* child, int* parentcnt) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i < n) leaf[i] = id[i];
+    if (i >= n - 1) return;
+    int l, r;
+    determine_range(mc, n, i, &l, &r);
+    int split = find_split(mc, l, r);
+    int lhs = split; if (lhs != l) lhs += n;
+    int rhs = split + 1; if (rhs != r) rhs += n;
+    child[i] = make_int2(lhs, rhs);
+    if (lhs >= 0 && lhs < 2 * n) atomicAdd(&parentcnt[lhs], 1);
+    if (rhs >= 0 && rhs < 2 * n) atomicAdd(&parentcnt[rhs], 1);
+}
+
+// lbvh.py:155-158 getBoundingBox
+__device__ __forceinline__ void face_box(const float* __restrict__ verts, int face, V3* lo, V3* hi) {
+    V3 a = face_vertex(verts, face, 0), b = face_vertex(verts, face, 1), c = face_vertex(verts, face, 2);
+    *lo = vmin(vmin(a, b), c); *hi = vmax(vmax(a, b), c);
+}
+
+// lbvh.py:272-294 genAABBSubstep as a Jacobi sweep: a node becomes ready in sweep `stamp` iff both children
+// were ready BEFORE this sweep (stamp < current), so there is no intra-sweep race.  Also carries the slot range
+// and height used for validation.
+__global__ void __launch_bounds__(BLK) k_aabb_sweep(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child, int n, int stamp,
+                                                    float* bmin, float* bmax, int* ready, int2* range, int* height, int* scal) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    if (ready[i] != 0) return;
+    int2 ch = child[i];
+    V3 lo[2], hi[2]; int2 rg[2]; int hg[2];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int c = k == 0 ? ch.x : ch.y;
+        if (c < 0 || c >= 2 * n - 1) { ok = false; break; }
+        if (c < n) {
+            face_box(verts, leaf[c], &lo[k], &hi[k]);
+            rg[k] = make_int2(c, c); hg[k] = 1;
+        } else {
+            int j = c - n;
+            int st = ready[j];
+            if (st == 0 || st >= stamp) { ok = false; break; }
+            lo[k] = mk3(bmin[3 * j], bmin[3 * j + 1], bmin[3 * j + 2]);
+            hi[k] = mk3(bmax[3 * j], bmax[3 * j + 1], bmax[3 * j + 2]);
+            rg[k] = range[j]; hg[k] = height[j];
+        }
+    }
+    if (!ok) { atomicAdd(&scal[8], 1); return; }
+    V3 l = vmin(lo[0], lo[1]), h = vmax(hi[0], hi[1]);
+    bmin[3 * i] = l.x; bmin[3 * i + 1] = l.y; bmin[3 * i + 2] = l.z;
+    bmax[3 * i] = h.x; bmax[3 * i + 1] = h.y; bmax[3 * i + 2] = h.z;
+    range[i] = make_int2(min(rg[0].x, rg[1].x), max(rg[0].y, rg[1].y));
+    height[i] = 1 + max(hg[0], hg[1]);
+    if (!(rg[0].y < rg[1].x)) scal[9] = 1;     // child0 must cover lower slots than child1
+    if (i == 0) scal[10] = height[i];
+    ready[i] = stamp;
+}
+
+__global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parentcnt, int n, int* scal) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= 2 * n - 1) return;
+    int want = (i == n) ? 0 : 1;
+    if (parentcnt[i] != want) scal[9] = 1;
+}
+
+// packed 64-byte node: both children's boxes (leaf child: the triangle's bounds)
+__global__ void __launch_bounds__(BLK) k_pack_nodes(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child,
+                                                    const float* __restrict__ bmin, const float* __restrict__ bmax, int n, Node64* nodes) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    int2 ch = child[i];
+    V3 lo[2], hi[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int c = k == 0 ? ch.x : ch.y;
+        if (c < 0 || c >= 2 * n - 1) { lo[k] = v3s(0.0f); hi[k] = v3s(0.0f); }
+        else if (c < n) face_box(verts, leaf[c], &lo[k], &hi[k]);
+        else { int j = c - n; lo[k] = mk3(bmin[3 * j], bmin[3 * j + 1], bmin[3 * j + 2]); hi[k] = mk3(bmax[3 * j], bmax[3 * j + 1], bmax[3 * j + 2]); }
+    }
+    Node64 N;
+    N.a = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ch.x));
+    N.b = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(ch.y));
+    N.c = make_float4(lo[1].x, lo[1].y, lo[1].z, 0.0f);
+    N.d = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.0f);
+    nodes[i] = N;
+}
+
+// packed 64-byte triangle by leaf slot; u, v, n, uu, uv, vv are the f32 expressions of geometries.py:121-137
+__global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ verts, const int* __restrict__ leaf, int n, Tri64* tris) {
+    int s = blockIdx.x * BLK + threadIdx.x;
+    if (s >= n) return;
+    int f = leaf[s];
+    V3 v0 = face_vertex(verts, f, 0), v1 = face_vertex(verts, f, 1), v2 = face_vertex(verts, f, 2);
+    V3 u = v1 - v0, v = v2 - v0;
+    V3 nrm = cross(u, v);
+    Tri64 T;
+    T.a = make_float4(v0.x, v0.y, v0.z, __int_as_float(f));
+    T.b = make_float4(u.x, u.y, u.z, dot(u, u));
+    T.c = make_float4(v.x, v.y, v.z, dot(u, v));
+    T.d = make_float4(nrm.x, nrm.y, nrm.z, dot(v, v));
+    tris[s] = T;
+}
+
+inline int nblk(int n) { return (n + BLK - 1) / BLK; }
+
+}  // namespace
+
+int ptb_lbvh_build(ptb_ctx* c) {
+    const int n = c->nfaces;
+    cudaStream_t st = c->stream;
+    c->tree_n = n;
+    c->tree_info = ptb_tree_info{};
+    c->tree_info.n = n;
+    cudaEvent_t e0, e1;
+    PTB_CUDA(cudaEventCreate(&e0)); PTB_CUDA(cudaEventCreate(&e1));
+    PTB_CUDA(cudaEventRecord(e0, st));
+    float* scal = (float*)c->d_scalars;
+    int nint = n > 1 ? n - 1 : 1;
+    k_init_scalars<<<1, 1, 0, st>>>(scal);
+    PTB_CUDA(cudaMemsetAsync(c->d_child, 0, sizeof(int2) * nint, st));
+    PTB_CUDA(cudaMemsetAsync(c->d_bmin, 0, sizeof(float) * 3 * nint, st));
+    PTB_CUDA(cudaMemsetAsync(c->d_bmax, 0, sizeof(float) * 3 * nint, st));
+    PTB_CUDA(cudaMemsetAsync(c->d_ready, 0, sizeof(int) * nint, st));
+    PTB_CUDA(cudaMemsetAsync(c->d_parentcnt, 0, sizeof(int) * 2 * (size_t)(n > 0 ? n : 1), st));
+    int sweeps = 1, valid = 0, depth = 0;
+    if (n > 0) {
+        int grid = nblk(n) < c->sm_count * 8 ? nblk(n) : c->sm_count * 8;
+        k_center_bounds<<<grid, BLK, 0, st>>>(c->d_verts, n, scal);
+        k_morton<<<nblk(n), BLK, 0, st>>>(c->d_verts, n, scal, c->d_mc_tmp, c->d_id_tmp);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, c->d_mc_tmp, c->d_mc, c->d_id_tmp, c->d_id, n, 0, 30, st);
+        if (need > c->sort_tmp_bytes) {
+            if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
+            PTB_CUDA(cudaMalloc(&c->d_sort_tmp, need));
+            c->sort_tmp_bytes = need;
+        }
+        PTB_CUDA(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, need, c->d_mc_tmp, c->d_mc, c->d_id_tmp, c->d_id, n, 0, 30, st));
+        k_hierarchy<<<nblk(n), BLK, 0, st>>>(c->d_mc, c->d_id, n, c->d_leaf, c->d_child, c->d_parentcnt);
+        c->launches += 5;
+    }
+    if (n > 1) {
+        // genAABBs lbvh.py:251-261: sweep until every node is ready, give up after 64
+        int first_check = 1;
+        while ((1 << first_check) < n) first_check++;   // a tree over n leaves is at least log2(n) high
+        int remaining = -1;
+        int h_scal[16];
+        for (sweeps = 1; sweeps <= 64; sweeps++) {
+            PTB_CUDA(cudaMemsetAsync(&c->d_scalars[8], 0, sizeof(int), st));
+            k_aabb_sweep<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, n, sweeps, c->d_bmin, c->d_bmax, c->d_ready, c->d_range, c->d_height, c->d_scalars);
+            c->launches++;
+            if (sweeps >= first_check - 1 || sweeps == 64) {
+                PTB_CUDA(cudaMemcpyAsync(h_scal, c->d_scalars, sizeof h_scal, cudaMemcpyDeviceToHost, st));
+                PTB_CUDA(cudaStreamSynchronize(st));
+                remaining = h_scal[8];
+                if (remaining == 0) break;
+            }
+        }
+        if (remaining != 0) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            c->tree_info.aabb_sweeps = sweeps;
+            ptb_set_error("AABB step never stop! hierarchy corrupted?");
+            return 2;
+        }
+        k_validate<<<nblk(2 * n - 1), BLK, 0, st>>>(c->d_parentcnt, n, c->d_scalars);
+        k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, c->d_bmin, c->d_bmax, n, c->d_nodes);
+        c->launches += 2;
+    }
+    if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris); c->launches++; }
+    PTB_CUDA(cudaEventRecord(e1, st));
+    {
+        int h_scal[16];
+        PTB_CUDA(cudaMemcpyAsync(h_scal, c->d_scalars, sizeof h_scal, cudaMemcpyDeviceToHost, st));
+        float h_root[6] = {0, 0, 0, 0, 0, 0};
+        if (n > 1) {
+            PTB_CUDA(cudaMemcpyAsync(h_root, c->d_bmin, 12, cudaMemcpyDeviceToHost, st));
+            PTB_CUDA(cudaMemcpyAsync(h_root + 3, c->d_bmax, 12, cudaMemcpyDeviceToHost, st));
+        }
+        PTB_CUDA(cudaStreamSynchronize(st));
+        valid = (n > 1) && h_scal[9] == 0;
+        depth = valid ? h_scal[10] : 0;
+        for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
+    }
+    PTB_CUDA(cudaGetLastError());
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->tree_info.aabb_sweeps = sweeps;
+    c->tree_info.valid = valid;
+    c->tree_info.depth = depth;
+    c->tree_info.build_ms = ms;
+    c->tree_info.policy = ptb_effective_policy(c, c->traversal_request);
+    return 0;
+}

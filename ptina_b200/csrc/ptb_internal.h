@@ -1,0 +1,138 @@
+// ptb_internal.h -- context layout and the launch functions shared between api.cu, lbvh.cu, wavefront.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/ptina_b200.h"
+#include "ptb_shade.cuh"
+#include "ptb_traverse.cuh"
+
+#define PTB_SOBOL_ROWS 21
+
+void ptb_set_error(const char* fmt, ...);
+#define PTB_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ptb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+// SoA wavefront state, one entry per path in flight (HBM; 7 x 16 B per path)
+struct PathState {
+    float4* ray_o;    // origin xyz, w = last_brdf_pdf            (path.py:22,61)
+    float4* ray_d;    // direction xyz, w = avoid id (int bits)   (path.py:19,40)
+    float4* hit;      // depth, u, v, face id (int bits; -1 = miss)
+    float4* thr;      // throughput rgb (path.py:21), w = depth counter (int bits)
+    float4* result;   // radiance rgb (path.py:20)
+    float4* sh_d;     // shadow ray direction xyz, w = distance to the light sample
+    float4* sh_c;     // contribution to add if the shadow ray is unoccluded
+};
+
+// device-side control block: queue sizes and work cursors
+struct Ctrl {
+    int n_in;        // entries in the active queue being consumed
+    int n_out;       // entries appended to the next active queue
+    int n_shadow;    // entries in the shadow queue
+    int cur_extend, cur_shadow;
+    int pad[3];
+};
+
+struct DevCounters {
+    unsigned long long extend_rays, shadow_rays, nodes, boxes, tris, paths;
+    unsigned int max_stack, pad;
+};
+
+enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_ACCUM, ST_COUNT };
+
+struct StageEvent { int stage; cudaEvent_t a, b; };
+
+struct ptb_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    ptb_caps caps{};
+    int sm_count = 148;
+
+    // ---- scene (reference layout) ----
+    int nfaces = 0;
+    float* d_verts = nullptr;       // [nfaces*3][8]   model.py:14
+    int32_t* d_mtlids = nullptr;    // [nfaces]        model.py:15
+    float4* d_texels = nullptr;     // arena           image.py:17
+    SceneParams h_params{};         // host mirror
+    SceneParams* d_params = nullptr;
+    bool params_dirty = true;
+    float h_w2v[16]{};
+
+    // ---- sobol ----
+    int32_t* d_sobolV = nullptr;    // [21][dim]
+    int sobol_dim = 0;
+    int sobol_time = 0;
+    float* d_sobolP = nullptr;      // [spp_batch][dim] points of the batch in flight
+    int sobolP_cap = 0;
+
+    // ---- tree (reference arrays, lbvh.py:50-59) + packed traversal data ----
+    int tree_n = 0;
+    int32_t *d_mc = nullptr, *d_id = nullptr, *d_mc_tmp = nullptr, *d_id_tmp = nullptr, *d_leaf = nullptr;
+    int2* d_child = nullptr;
+    float *d_bmin = nullptr, *d_bmax = nullptr;
+    int32_t* d_ready = nullptr;     // sweep stamp per internal node
+    int32_t* d_parentcnt = nullptr; // reference counts for validation [2n]
+    int2* d_range = nullptr;        // (min slot, max slot) per internal node
+    int32_t* d_height = nullptr;
+    Node64* d_nodes = nullptr;
+    Tri64* d_tris = nullptr;
+    void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
+    int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)
+    ptb_tree_info tree_info{};
+    int traversal_request = PTB_TRAVERSE_AUTO;
+    float root_lo[3]{}, root_hi[3]{};
+
+    // ---- film (filmtable.py:12-14) ----
+    int nx = 0, ny = 0;
+    float4* d_film = nullptr;       // [passes][max_filmsize]
+
+    // ---- wavefront ----
+    int64_t max_paths = 0;
+    PathState st{};
+    int* d_queue[2] = {nullptr, nullptr};
+    int* d_shadowq = nullptr;
+    Ctrl* d_ctrl = nullptr;
+    DevCounters* d_counters = nullptr;
+    int counting = 0;
+    int blocks_extend = 0, blocks_shadow = 0, blocks_generic = 0;
+    std::vector<StageEvent> events;
+    std::vector<cudaEvent_t> event_pool;
+    int profiling = 0;
+    float stage_ms[ST_COUNT]{};
+    long long launches = 0;
+
+    // ---- MLT (mltpath.py:9-36) ----
+    float *d_Xold = nullptr, *d_Xnew = nullptr;   // [nchains][32]
+    float4* d_Lold = nullptr;                      // [nchains]
+    int mlt_first = 0, mlt_count = 0;
+    uint64_t mlt_seed = 0; uint32_t mlt_iter = 0;
+    float mlt_lsp = 0.25f, mlt_sigma = 0.01f;
+};
+
+TraceScene ptb_trace_scene(const ptb_ctx* c);
+int ptb_effective_policy(const ptb_ctx* c, int requested);
+
+// lbvh.cu
+int ptb_lbvh_build(ptb_ctx* c);
+// wavefront.cu
+int ptb_wf_init(ptb_ctx* c);
+int ptb_wf_upload_params(ptb_ctx* c);
+int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev);
+int ptb_wf_sobol_points(ptb_ctx* c, int k_first, int count, int stride, float* P_dev);
+int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
+int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev, const float* dis_dev, int m, int policy, int anyhit,
+                     int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
+int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
+int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev);
+int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
+int ptb_wf_mlt_reset(ptb_ctx* c);
+void ptb_stage_begin(ptb_ctx* c, int stage);
+void ptb_stage_end(ptb_ctx* c);
+int ptb_stage_collect(ptb_ctx* c);

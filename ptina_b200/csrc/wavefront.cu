@@ -1,0 +1,809 @@
+// wavefront.cu -- the per-pixel path-tracing hot path as a wavefront pipeline.
+//
+// The reference runs one divergent megakernel per sample (engine/path.py:79-83 `_render` -> do_render path.py:85-93 ->
+// path_trace path.py:18-64; engine/brute.py:29-75; engine/mltpath.py:54-83).  Here the same per-path arithmetic is
+// split into stages that each keep warps on one code path, with path state in HBM (PathState, SoA) and
+// compacted index queues between stages:
+//
+//   sobol_points -> raygen -> [ extend -> shade -> shadow ] x 5 bounces -> accumulate
+//
+//   raygen   : Sobol jitter (sobol.py:107-125), Camera.generate (camera.py:34-39)
+//   extend   : closest hit (lbvh.py:313-347), persistent warps pulling 32-ray chunks from the queue
+//   shade    : light hit + MIS, miss -> environment, shading frame, material fetch, NEE sample -> shadow queue,
+//              Disney bounce -> next active queue (queues compacted with warp ballot + block prefix)
+//   shadow   : any-hit occlusion, adds the pending NEE contribution
+//   accumulate: film[0, x, y] += (rgb, 1) per sample in Sobol order (path.py:93) -- deterministic, no atomics
+//
+// Random numbers: draw c of pixel (i,j) at Sobol point k is P_k[(wanghash2(i,j) + c) mod 21201]; the draw index is a
+// pure function of the bounce number (2 jitter draws, then 3 NEE + 3 bounce draws per bounce), so no per-path
+// generator state is carried.
+#include <cstdio>
+#include "ptb_internal.h"
+
+namespace {
+
+constexpr int BLK = 128;
+
+// ---- pixel <-> path-slot mapping: a warp owns an 8x4 pixel tile so primary rays stay coherent -----------------
+struct FrameMap { int nx, ny, tiles_y, pps; };   // pps = path slots per sample (multiple of 32)
+__host__ __device__ inline FrameMap make_frame(int nx, int ny) {
+    FrameMap f; f.nx = nx; f.ny = ny;
+    int tx = (nx + 7) / 8; f.tiles_y = (ny + 3) / 4;
+    f.pps = tx * f.tiles_y * 32;
+    return f;
+}
+PTB_D bool slot_pixel(const FrameMap& f, int q, int* x, int* y) {
+    int tile = q >> 5, lane = q & 31;
+    int tx = tile / f.tiles_y, ty = tile - tx * f.tiles_y;
+    *x = tx * 8 + (lane >> 2);
+    *y = ty * 4 + (lane & 3);
+    return *x < f.nx && *y < f.ny;
+}
+
+// ---- random source: Sobol table of the path's sample (sobol.py:107-125) or the MLT chain vector (sampling/__init__.py:53-64)
+struct Rng {
+    const float* __restrict__ tab;
+    int base, dim;   // dim == 0 -> direct indexing (MLT)
+    PTB_D float draw(int c) const {
+        if (dim == 0) return tab[c];
+        int i = (int)((unsigned)base + (unsigned)c);   // i32 wrap of `self.i += 1`
+        return __ldg(&tab[pymod(i, dim)]);
+    }
+};
+
+// ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
+PTB_D void block_append(bool flag, int value, int* __restrict__ queue, int* counter, int* s_warp, int* s_base) {
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[w] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < BLK / 32; i++) { int c = s_warp[i]; s_warp[i] = tot; tot += c; }
+        *s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    if (flag) queue[*s_base + s_warp[w] + rank] = value;
+    __syncthreads();
+}
+
+// ---- sampling/sobol.py:99-105 in closed form: X_k = XOR_{b in gray(k)} V[b+1];  P = X / 2^32 (sobol.py:19-29) ---------
+__global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, int count, int stride, float* __restrict__ P) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    for (int s = 0; s < count; s++) {
+        unsigned k = (unsigned)(k_first + s * stride);
+        unsigned g = k ^ (k >> 1), X = 0;
+        for (int b = 0; b < 20; b++) if ((g >> b) & 1u) X ^= (unsigned)V[(b + 1) * dim + j];
+        // only the top 20 bits are ever set, so the MSB-first sum of construct_float is this exact product
+        P[(size_t)s * dim + j] = (float)X * 2.3283064365386963e-10f;
+    }
+}
+
+__global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
+__global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
+
+// ---- path.py:85-93 do_render (first half) / brute.py:66-73 -----------------------------------------------------------
+__global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ P, const float* __restrict__ sobolP, int dim, FrameMap fm, int nsamp,
+                                                PathState st, int* __restrict__ queue, Ctrl* ctrl, DevCounters* ctr) {
+    __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
+    int total = fm.pps * nsamp;
+    int rounded = (total + BLK - 1) / BLK * BLK;
+    for (int p0 = blockIdx.x * BLK; p0 < rounded; p0 += gridDim.x * BLK) {
+        int p = p0 + threadIdx.x;
+        bool live = false;
+        if (p < total) {
+            int s = p / fm.pps, q = p - s * fm.pps;
+            int x, y;
+            if (slot_pixel(fm, q, &x, &y)) {
+                live = true;
+                Rng rng; rng.tab = sobolP + (size_t)s * dim; rng.base = wanghash2(x, y); rng.dim = dim;
+                float dx = rng.draw(0), dy = rng.draw(1);
+                float fx = ((float)x + dx) / (float)fm.nx * 2.0f - 1.0f;
+                float fy = ((float)y + dy) / (float)fm.ny * 2.0f - 1.0f;
+                V3 ro, rd;
+                camera_generate(P, fx, fy, &ro, &rd);
+                st.ray_o[p] = make_float4(ro.x, ro.y, ro.z, 0.0f);                         // last_brdf_pdf = 0
+                st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));           // avoid = -1
+                st.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));              // depth = 0
+                st.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        block_append(live, p, queue, &ctrl->n_in, s_warp, &s_base);
+    }
+    if (ctr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->paths, (unsigned long long)nsamp * fm.nx * fm.ny);
+}
+
+// ---- extend: closest hit for every queued path (path.py:28-29) ------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(BLK) k_extend(TraceScene S, PathState st, const int* __restrict__ queue, Ctrl* ctrl, int policy, DevCounters* ctr) {
+    const int lane = threadIdx.x & 31;
+    const int count = ctrl->n_in;
+    TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
+    unsigned long long nrays = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctrl->cur_extend, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        int idx = base + lane;
+        if (idx < count) {
+            int p = queue[idx];
+            float4 o4 = st.ray_o[p], d4 = st.ray_d[p];
+            V3 ro = mk3(o4.x, o4.y, o4.z);
+            V3 rd = normalized(mk3(d4.x, d4.y, d4.z));    // path.py:28  r.d = r.d.normalized()
+            int avoid = __float_as_int(d4.w);
+            HitRec h = policy == PTB_TRAVERSE_REFERENCE ? trace_reference<COUNT>(S, ro, rd, avoid, &C)
+                                                        : trace_ordered<false, COUNT>(S, ro, rd, avoid, PTB_INF, &C);
+            st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, d4.w);
+            st.hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1));
+            if (COUNT) nrays++;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            C.nodes += __shfl_xor_sync(0xffffffffu, C.nodes, o); C.boxes += __shfl_xor_sync(0xffffffffu, C.boxes, o);
+            C.tris += __shfl_xor_sync(0xffffffffu, C.tris, o); nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
+            C.max_stack = max(C.max_stack, __shfl_xor_sync(0xffffffffu, C.max_stack, o));
+        }
+        if (lane == 0) {
+            atomicAdd(&ctr->nodes, C.nodes); atomicAdd(&ctr->boxes, C.boxes); atomicAdd(&ctr->tris, C.tris);
+            atomicAdd(&ctr->extend_rays, nrays); atomicMax(&ctr->max_stack, C.max_stack);
+        }
+    }
+}
+
+// ---- shadow: occlusion of the queued NEE rays (path.py:49-55) -----------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(BLK) k_shadow(TraceScene S, PathState st, const int* __restrict__ queue, Ctrl* ctrl, int policy, DevCounters* ctr) {
+    const int lane = threadIdx.x & 31;
+    const int count = ctrl->n_shadow;
+    TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
+    unsigned long long nrays = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctrl->cur_shadow, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        int idx = base + lane;
+        if (idx < count) {
+            int p = queue[idx];
+            float4 o4 = st.ray_o[p], d4 = st.sh_d[p];
+            V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);   // Ray(hitpos, li.dir): NOT re-normalised
+            int avoid = __float_as_int(st.ray_d[p].w);
+            float dis = d4.w;
+            bool occluded;
+            if (policy == PTB_TRAVERSE_REFERENCE) {
+                HitRec h = trace_reference<COUNT>(S, ro, rd, avoid, &C);
+                occluded = !(h.hit == 0 || h.depth > dis);
+            } else {
+                HitRec h = trace_ordered<true, COUNT>(S, ro, rd, avoid, dis, &C);
+                occluded = h.hit != 0;
+            }
+            if (!occluded) {
+                float4 r = st.result[p], c4 = st.sh_c[p];
+                st.result[p] = make_float4(r.x + c4.x, r.y + c4.y, r.z + c4.z, r.w);
+            }
+            if (COUNT) nrays++;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            C.nodes += __shfl_xor_sync(0xffffffffu, C.nodes, o); C.boxes += __shfl_xor_sync(0xffffffffu, C.boxes, o);
+            C.tris += __shfl_xor_sync(0xffffffffu, C.tris, o); nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
+            C.max_stack = max(C.max_stack, __shfl_xor_sync(0xffffffffu, C.max_stack, o));
+        }
+        if (lane == 0) {
+            atomicAdd(&ctr->nodes, C.nodes); atomicAdd(&ctr->boxes, C.boxes); atomicAdd(&ctr->tris, C.tris);
+            atomicAdd(&ctr->shadow_rays, nrays); atomicMax(&ctr->max_stack, C.max_stack);
+        }
+    }
+}
+
+// ---- model.py:88-101 get_geometries + geometries.py:96-108 -------------------------------------------------------------------
+PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict__ mtlids, int f, float u, float v, V3 ro, V3 rd, float depth,
+                         V3* hitpos, V3* normal, float* tu, float* tv, int* mtlid) {
+    const float4* p = reinterpret_cast<const float4*>(verts + (size_t)f * 24);   // 3 corners x (pos3 nrm3 uv2) = 6 x float4
+    float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3), c0 = __ldg(p + 4), c1 = __ldg(p + 5);
+    float wx = 1.0f - u - v, wy = u, wz = v;
+    V3 n0 = mk3(a0.w, a1.x, a1.y), n1 = mk3(b0.w, b1.x, b1.y), n2 = mk3(c0.w, c1.x, c1.y);
+    V3 nrm = normalized(wx * n0 + wy * n1 + wz * n2);
+    *tu = wx * a1.z + wy * b1.z + wz * c1.z;
+    *tv = wx * a1.w + wy * b1.w + wz * c1.w;
+    *hitpos = ro + depth * rd;
+    float sg = -dot(rd, nrm);
+    if (sg < 0.0f) nrm = -nrm;
+    *normal = nrm;
+    *mtlid = __ldg(&mtlids[f]);
+}
+
+// ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
+template <int ENGINE>
+__global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
+                                               const int* __restrict__ mtlids, const float* __restrict__ rngtab, int dim, int rng_stride, FrameMap fm,
+                                               PathState st, const int* __restrict__ q_in, int* __restrict__ q_out, int* __restrict__ q_shadow, Ctrl* ctrl) {
+    __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
+    const int count = ctrl->n_in;
+    const int rounded = (count + BLK - 1) / BLK * BLK;
+    for (int i0 = blockIdx.x * BLK; i0 < rounded; i0 += gridDim.x * BLK) {
+        int idx = i0 + threadIdx.x;
+        bool alive = false, want_shadow = false;
+        int p = -1;
+        if (idx < count) {
+            p = q_in[idx];
+            float4 o4 = st.ray_o[p], d4 = st.ray_d[p], h4 = st.hit[p], t4 = st.thr[p], r4 = st.result[p];
+            V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
+            V3 thr = mk3(t4.x, t4.y, t4.z), result = mk3(r4.x, r4.y, r4.z);
+            float last_pdf = o4.w;
+            int depth = __float_as_int(t4.w) + 1;                       // path.py:26 depth += 1
+            int hit_index = __float_as_int(h4.w);
+            bool hit = hit_index >= 0;
+            Rng rng;
+            if (dim == 0) { rng.tab = rngtab + (size_t)p * rng_stride; rng.base = 0; rng.dim = 0; }
+            else {
+                int s = p / fm.pps, q = p - s * fm.pps, x, y;
+                slot_pixel(fm, q, &x, &y);
+                rng.tab = rngtab + (size_t)s * dim; rng.base = wanghash2(x, y); rng.dim = dim;
+            }
+            // path.py:31-35 / brute.py:41-43
+            LitHit lit = light_hit(P, ro, rd);
+            if (lit.hit != 0 && (!hit || lit.dis < h4.x)) {
+                if (ENGINE == PTB_ENGINE_PATH) {
+                    float mis = power_heuristic(last_pdf, lit.pdf);
+                    result = result + thr * (mis * lit.color);
+                } else {
+                    result = result + thr * lit.color;
+                }
+            }
+            if (!hit) {
+                result = result + thr * world_at(P, texels, rd);        // path.py:37-39
+            } else {
+                V3 hitpos, normal; float tu, tv; int mtlid;
+                shading_frame(verts, mtlids, hit_index, h4.y, h4.z, ro, rd, h4.x, &hitpos, &normal, &tu, &tv, &mtlid);
+                Disney mat = material_get(P, texels, mtlid, tu, tv);
+                float sign = -dot(rd, normal);                            // path.py:44-46 (recomputed on the flipped normal)
+                if (sign < 0.0f) normal = -normal;
+                V3 wi = -rd;
+                int c0;
+                if (ENGINE == PTB_ENGINE_PATH) {
+                    c0 = 2 + 6 * (depth - 1);
+                    // path.py:48-56 next-event estimation
+                    V3 ls = mk3(rng.draw(c0), rng.draw(c0 + 1), rng.draw(c0 + 2));
+                    LitSample li = light_sample(P, hitpos, ls);
+                    if (any_gt(li.color, 0.0f)) {
+                        V3 brdf_clr = disney_brdf(mat, normal, sign, wi, li.dir);
+                        float brdf_pdf = vavg(brdf_clr);                  // sic: path.py:53
+                        float mis = power_heuristic(li.pdf, brdf_pdf);
+                        V3 direct = mis * li.color * brdf_clr * dot_or_zero(normal, li.dir);
+                        V3 contrib = thr * direct;
+                        st.sh_d[p] = make_float4(li.dir.x, li.dir.y, li.dir.z, li.dis);
+                        st.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+                        want_shadow = true;
+                    }
+                    c0 += 3;
+                } else {
+                    c0 = 2 + 3 * (depth - 1);
+                }
+                // path.py:58-62 / brute.py:56-60
+                BSDFSample bs = disney_bounce(mat, normal, sign, wi, mk3(rng.draw(c0), rng.draw(c0 + 1), rng.draw(c0 + 2)));
+                thr = thr * bs.color;
+                st.ray_o[p] = make_float4(hitpos.x, hitpos.y, hitpos.z, bs.pdf);
+                st.ray_d[p] = make_float4(bs.outdir.x, bs.outdir.y, bs.outdir.z, __int_as_float(hit_index));   // avoid = hit.index
+                st.thr[p] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
+                // loop condition path.py:25 / brute.py:35
+                if (ENGINE == PTB_ENGINE_PATH) alive = depth < 5 && any_gt(thr, 0.0f) && any_ne0(bs.outdir);
+                else alive = depth < 5 && any_gt(thr, PTB_EPS);
+            }
+            st.result[p] = make_float4(result.x, result.y, result.z, 0.0f);
+        }
+        block_append(alive, p, q_out, &ctrl->n_out, s_warp, &s_base);
+        if (ENGINE == PTB_ENGINE_PATH) block_append(want_shadow, p, q_shadow, &ctrl->n_shadow, s_warp, &s_base);
+    }
+}
+
+// ---- preview.py:23-41: primary hit -> albedo into pass 1, shading normal into pass 2 ---------------------------------------------
+__global__ void __launch_bounds__(BLK) k_preview(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
+                                                 const int* __restrict__ mtlids, FrameMap fm, int nsamp, PathState st, float4* __restrict__ film1, float4* __restrict__ film2) {
+    int q = blockIdx.x * BLK + threadIdx.x;
+    if (q >= fm.pps) return;
+    int x, y;
+    if (!slot_pixel(fm, q, &x, &y)) return;
+    size_t pix = (size_t)x * fm.ny + y;
+    float4 a = film1[pix], b = film2[pix];
+    for (int s = 0; s < nsamp; s++) {
+        int p = s * fm.pps + q;
+        float4 o4 = st.ray_o[p], d4 = st.ray_d[p], h4 = st.hit[p];
+        V3 albedo = v3s(0.0f), normal = v3s(0.0f);
+        int hit_index = __float_as_int(h4.w);
+        if (hit_index >= 0) {
+            V3 hitpos; float tu, tv; int mtlid;
+            shading_frame(verts, mtlids, hit_index, h4.y, h4.z, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), h4.x, &hitpos, &normal, &tu, &tv, &mtlid);
+            albedo = material_get(P, texels, mtlid, tu, tv).basecolor;
+        }
+        a = make_float4(a.x + albedo.x, a.y + albedo.y, a.z + albedo.z, a.w + 1.0f);
+        b = make_float4(b.x + normal.x, b.y + normal.y, b.z + normal.z, b.w + 1.0f);
+    }
+    film1[pix] = a; film2[pix] = b;
+}
+
+// ---- path.py:93: FilmTable()[0, i, j] += V34(clr, 1.0), samples folded in Sobol order ------------------------------------------------
+__global__ void __launch_bounds__(BLK) k_accumulate(float4* __restrict__ film, const float4* __restrict__ result, FrameMap fm, int nsamp, float* __restrict__ sample_out) {
+    int q = blockIdx.x * BLK + threadIdx.x;
+    if (q >= fm.pps) return;
+    int x, y;
+    if (!slot_pixel(fm, q, &x, &y)) return;
+    size_t pix = (size_t)x * fm.ny + y;
+    if (sample_out) {   // tap: radiance of the first sample, film untouched
+        float4 r = result[q];
+        sample_out[3 * pix] = r.x; sample_out[3 * pix + 1] = r.y; sample_out[3 * pix + 2] = r.z;
+        return;
+    }
+    float4 f = film[pix];
+    for (int s = 0; s < nsamp; s++) {
+        float4 r = result[(size_t)s * fm.pps + q];
+        f = make_float4(f.x + r.x, f.y + r.y, f.z + r.z, f.w + 1.0f);
+    }
+    film[pix] = f;
+}
+
+// ---- filmtable.py:47-79 resolve -----------------------------------------------------------------------------------------------------------
+// mode 0: get_image -> out[x][y][4];  mode 1: fast_export_image -> out[(y*nx+x)*3];  mode 2: raw copy
+__global__ void __launch_bounds__(BLK) k_resolve(const float4* __restrict__ film, int nx, int ny, int mode, float* __restrict__ out) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= nx * ny) return;
+    float4 v = film[i];
+    if (mode == 2) { reinterpret_cast<float4*>(out)[i] = v; return; }
+    int x = i / ny, y = i - x * ny;
+    if (mode == 0) {
+        if (v.w != 0.0f) v = make_float4(v.x / v.w, v.y / v.w, v.z / v.w, 1.0f);
+        else v = make_float4(0.9f, 0.4f, 0.9f, 0.0f);
+        reinterpret_cast<float4*>(out)[i] = v;
+    } else {
+        if (v.w != 0.0f) { v.x /= v.w; v.y /= v.w; v.z /= v.w; }
+        else { v.x = 0.9f; v.y = 0.4f; v.z = 0.9f; }
+        size_t base = ((size_t)y * nx + x) * 3;
+        out[base] = v.x; out[base + 1] = v.y; out[base + 2] = v.z;
+    }
+}
+
+// ---- taps ----------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK) k_gather_primary(FrameMap fm, PathState st, float* rays, int* hit, float* depth, int* index, float* uv, int which) {
+    int q = blockIdx.x * BLK + threadIdx.x;
+    if (q >= fm.pps) return;
+    int x, y;
+    if (!slot_pixel(fm, q, &x, &y)) return;
+    size_t pix = (size_t)x * fm.ny + y;
+    if (which == 0) {
+        float4 o = st.ray_o[q], d = st.ray_d[q];
+        rays[6 * pix] = o.x; rays[6 * pix + 1] = o.y; rays[6 * pix + 2] = o.z; rays[6 * pix + 3] = d.x; rays[6 * pix + 4] = d.y; rays[6 * pix + 5] = d.z;
+    } else {
+        float4 h = st.hit[q];
+        int id = __float_as_int(h.w);
+        if (hit) hit[pix] = id >= 0;
+        if (depth) depth[pix] = h.x;
+        if (index) index[pix] = id;
+        if (uv) { uv[2 * pix] = h.y; uv[2 * pix + 1] = h.z; }
+    }
+}
+
+__global__ void __launch_bounds__(BLK) k_intersect_tap(TraceScene S, const float* __restrict__ rays, const int* __restrict__ avoid, const float* __restrict__ dis, int m,
+                                                       int policy, int anyhit, int* hit, float* depth, int* index, float* uv) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    V3 ro = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), rd = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    int av = avoid ? avoid[i] : -1;
+    TraceCounters C;
+    HitRec h;
+    if (anyhit) {
+        float d = dis[i];
+        if (policy == PTB_TRAVERSE_REFERENCE) { h = trace_reference<false>(S, ro, rd, av, &C); hit[i] = !(h.hit == 0 || h.depth > d); }
+        else { h = trace_ordered<true, false>(S, ro, rd, av, d, &C); hit[i] = h.hit != 0; }
+        return;
+    }
+    h = policy == PTB_TRAVERSE_REFERENCE ? trace_reference<false>(S, ro, rd, av, &C) : trace_ordered<false, false>(S, ro, rd, av, PTB_INF, &C);
+    hit[i] = h.hit; depth[i] = h.depth; index[i] = h.index; uv[2 * i] = h.u; uv[2 * i + 1] = h.v;
+}
+
+PTB_D Disney disney_from(const float* p) {
+    Disney m;
+    m.basecolor = mk3(p[0], p[1], p[2]); m.metallic = p[3]; m.roughness = p[4]; m.specular = p[5]; m.specularTint = p[6];
+    m.subsurface = p[7]; m.sheen = p[8]; m.sheenTint = p[9]; m.clearcoat = p[10]; m.clearcoatGloss = p[11]; m.transmission = p[12]; m.ior = p[13];
+    disney_init(m);
+    return m;
+}
+// what: 0 eval_bsdf, 1 sample_bsdf, 2 material_get, 3 light_hit, 4 light_sample, 5 world_at
+__global__ void __launch_bounds__(BLK) k_shade_tap(const SceneParams* __restrict__ P, const float4* __restrict__ texels, int what, const float* __restrict__ in0,
+                                                   const float* __restrict__ in1, const int* __restrict__ ini, int m, float* __restrict__ out) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    if (what == 0 || what == 1) {
+        Disney d = disney_from(in0 + 14 * i);
+        const float* g = in1 + 10 * i;
+        V3 nrm = mk3(g[0], g[1], g[2]), wi = mk3(g[4], g[5], g[6]), x = mk3(g[7], g[8], g[9]);
+        if (what == 0) {
+            V3 r = disney_brdf(d, nrm, g[3], wi, x);
+            out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+        } else {
+            BSDFSample s = disney_bounce(d, nrm, g[3], wi, x);
+            float* o = out + 7 * i;
+            o[0] = s.outdir.x; o[1] = s.outdir.y; o[2] = s.outdir.z; o[3] = s.pdf; o[4] = s.color.x; o[5] = s.color.y; o[6] = s.color.z;
+        }
+    } else if (what == 2) {
+        Disney d = material_get(P, texels, ini[i], in0[2 * i], in0[2 * i + 1]);
+        float* o = out + 14 * i;
+        o[0] = d.basecolor.x; o[1] = d.basecolor.y; o[2] = d.basecolor.z; o[3] = d.metallic; o[4] = d.roughness; o[5] = d.specular; o[6] = d.specularTint;
+        o[7] = d.subsurface; o[8] = d.sheen; o[9] = d.sheenTint; o[10] = d.clearcoat; o[11] = d.clearcoatGloss; o[12] = d.transmission; o[13] = d.ior;
+    } else if (what == 3) {
+        const float* r = in0 + 6 * i;
+        LitHit l = light_hit(P, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]));
+        float* o = out + 6 * i;
+        o[0] = (float)l.hit; o[1] = l.dis; o[2] = l.pdf; o[3] = l.color.x; o[4] = l.color.y; o[5] = l.color.z;
+    } else if (what == 4) {
+        const float* r = in0 + 6 * i;
+        LitSample l = light_sample(P, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]));
+        float* o = out + 8 * i;
+        o[0] = l.dis; o[1] = l.dir.x; o[2] = l.dir.y; o[3] = l.dir.z; o[4] = l.pdf; o[5] = l.color.x; o[6] = l.color.y; o[7] = l.color.z;
+    } else {
+        V3 c = world_at(P, texels, mk3(in0[3 * i], in0[3 * i + 1], in0[3 * i + 2]));
+        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+    }
+}
+
+// L2-resident read bandwidth probe: every block streams the whole buffer with 16-byte loads
+__global__ void __launch_bounds__(256) k_l2_read(const float4* __restrict__ buf, size_t n4, int iters, float* sink) {
+    float acc = 0.0f;
+    for (int it = 0; it < iters; it++) {
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+            float4 v = __ldcg(&buf[i]);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    }
+    if (acc == 123456.789f) *sink = acc;
+}
+
+// ---- MLT (engine/mltpath.py:9-87) -----------------------------------------------------------------------------------------------------------
+// ti.random() is Taichi's per-thread xorshift stream, which cannot be reproduced; a counter-based Philox4x32-10 keyed by
+// (seed, chain, iteration) replaces it (statistical parity only).
+struct Philox {
+    uint32_t key[2], ctr[4], out[4]; int have;
+    PTB_D void init(uint64_t seed, uint32_t chain, uint32_t iter) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32); ctr[0] = 0; ctr[1] = chain; ctr[2] = iter; ctr[3] = 0x5054494eu; have = 0;
+    }
+    PTB_D void round_(uint32_t* c, uint32_t* k) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    PTB_D float next() {
+        if (have == 0) {
+            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+            for (int r = 0; r < 10; r++) { round_(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+            out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+            ctr[0]++; have = 4;
+        }
+        uint32_t v = out[--have];
+        return (float)(v >> 8) * 5.9604644775390625e-8f;   // [0, 1)
+    }
+};
+// common.py:337-352 erfinv (Winitzki, a = 0.147) and normaldist
+PTB_D float erfinv_ref(float x) {
+    float sgn = x < 0.0f ? -1.0f : 1.0f;
+    x = (1.0f - x) * (1.0f + x);
+    float lnx = logf(x);
+    float tt1 = (float)(2.0 / (3.14159265358979323846 * 0.147)) + 0.5f * lnx;
+    float tt2 = (float)(1.0 / 0.147) * lnx;
+    return sgn * sqrtf(-tt1 + sqrtf(tt1 * tt1 - tt2));
+}
+PTB_D float normaldist(float samp) { return 1.41421356237309504880f * erfinv_ref(samp * 2.0f - 1.0f); }
+PTB_D float pymodf1(float a) { float r = fmodf(a, 1.0f); if (r < 0.0f) r += 1.0f; return r; }   // Python-style `% 1`
+
+// mltpath.py:30-36 reset
+__global__ void __launch_bounds__(BLK) k_mlt_reset(float* Xold, float4* Lold, int nchains, int chain_first, uint64_t seed) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= nchains) return;
+    Philox g; g.init(seed, (uint32_t)(chain_first + i), 0xffffffffu);
+    Lold[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);   // L_old = 0, accum = 1
+    for (int j = 0; j < 32; j++) Xold[(size_t)i * 32 + j] = g.next();
+}
+// mltpath.py:56-74: mutate, then camera ray from the first two dims
+__global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restrict__ P, const float* __restrict__ Xold, float* __restrict__ Xnew, int nchains, int chain_first,
+                                                    uint64_t seed, uint32_t iter, float lsp, float sigma, PathState st, int* __restrict__ queue, Ctrl* ctrl, DevCounters* ctr) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= nchains) return;
+    Philox g; g.init(seed, (uint32_t)(chain_first + i), iter);
+    const float* xo = Xold + (size_t)i * 32; float* xn = Xnew + (size_t)i * 32;
+    if (g.next() < lsp) { for (int j = 0; j < 32; j++) xn[j] = g.next(); }
+    else { for (int j = 0; j < 32; j++) xn[j] = pymodf1(xo[j] + sigma * normaldist(g.next())); }
+    V3 ro, rd;
+    camera_generate(P, xn[0] * 2.0f - 1.0f, xn[1] * 2.0f - 1.0f, &ro, &rd);
+    st.ray_o[i] = make_float4(ro.x, ro.y, ro.z, 0.0f);
+    st.ray_d[i] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));
+    st.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
+    st.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    queue[i] = i;
+    if (i == 0) { ctrl->n_in = nchains; if (ctr) atomicAdd(&ctr->paths, (unsigned long long)nchains); }
+}
+// mltpath.py:47-52 splat + 75-81 accept/reject
+__global__ void __launch_bounds__(BLK) k_mlt_finish(float* __restrict__ Xold, const float* __restrict__ Xnew, float4* __restrict__ Lold, const float4* __restrict__ result,
+                                                    int nchains, int chain_first, uint64_t seed, uint32_t iter, int nx, int ny, float4* __restrict__ film) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= nchains) return;
+    float4 Ln4 = result[i], Lo4 = Lold[i];
+    V3 Ln = mk3(Ln4.x, Ln4.y, Ln4.z), Lo = mk3(Lo4.x, Lo4.y, Lo4.z);
+    float AL_new = vavg(Ln) + 1e-10f, AL_old = vavg(Lo) + 1e-10f;
+    float accept = fminf(1.0f, AL_new / AL_old);
+    V3 splat = Ln * Lo4.w;                                    // L_new * accum
+    const float* xn = Xnew + (size_t)i * 32;
+    int px = ifloor(xn[0] * (float)nx), py = ifloor(xn[1] * (float)ny);
+    if (px >= 0 && px < nx && py >= 0 && py < ny) {
+        float* f = reinterpret_cast<float*>(&film[(size_t)px * ny + py]);
+        atomicAdd(f, splat.x); atomicAdd(f + 1, splat.y); atomicAdd(f + 2, splat.z); atomicAdd(f + 3, 1.0f);
+    }
+    Philox g; g.init(seed ^ 0xA5A5A5A5DEADBEEFull, (uint32_t)(chain_first + i), iter);
+    if (g.next() < accept) {
+        Lold[i] = make_float4(Ln.x, Ln.y, Ln.z, Lo4.w);
+        for (int j = 0; j < 32; j++) Xold[(size_t)i * 32 + j] = xn[j];
+    }
+}
+
+inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
+
+}  // namespace
+
+// ================================================= host side ==========================================================
+void ptb_stage_begin(ptb_ctx* c, int stage) {
+    if (!c->profiling) return;
+    StageEvent ev; ev.stage = stage;
+    for (cudaEvent_t* e : {&ev.a, &ev.b}) {
+        if (!c->event_pool.empty()) { *e = c->event_pool.back(); c->event_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(ev.a, c->stream);
+    c->events.push_back(ev);
+}
+void ptb_stage_end(ptb_ctx* c) {
+    if (!c->profiling) return;
+    cudaEventRecord(c->events.back().b, c->stream);
+}
+int ptb_stage_collect(ptb_ctx* c) {
+    if (c->events.empty()) return 0;
+    PTB_CUDA(cudaEventSynchronize(c->events.back().b));
+    for (auto& ev : c->events) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
+        c->stage_ms[ev.stage] += ms;
+        c->event_pool.push_back(ev.a); c->event_pool.push_back(ev.b);
+    }
+    c->events.clear();
+    return 0;
+}
+
+int ptb_wf_init(ptb_ctx* c) {
+    int64_t np = c->max_paths;
+    float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result, &c->st.sh_d, &c->st.sh_c};
+    for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
+    PTB_CUDA(cudaMalloc(&c->d_queue[0], sizeof(int) * np));
+    PTB_CUDA(cudaMalloc(&c->d_queue[1], sizeof(int) * np));
+    PTB_CUDA(cudaMalloc(&c->d_shadowq, sizeof(int) * np));
+    PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
+    PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
+    PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+    PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
+    int occ = 0;
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, BLK, 0));
+    c->blocks_extend = c->sm_count * (occ > 0 ? occ : 4);
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<false>, BLK, 0));
+    c->blocks_shadow = c->sm_count * (occ > 0 ? occ : 4);
+    c->blocks_generic = c->sm_count * 8;
+    return 0;
+}
+
+int ptb_wf_upload_params(ptb_ctx* c) {
+    if (!c->params_dirty) return 0;
+    c->h_params.nx = c->nx; c->h_params.ny = c->ny;
+    // pageable host source: the copy is staged before the call returns, so later host edits cannot race it
+    PTB_CUDA(cudaMemcpyAsync(c->d_params, &c->h_params, sizeof(SceneParams), cudaMemcpyHostToDevice, c->stream));
+    c->params_dirty = false;
+    return 0;
+}
+
+int ptb_wf_sobol_points(ptb_ctx* c, int k_first, int count, int stride, float* P_dev) {
+    if (!c->d_sobolV) { ptb_set_error("Sobol direction table not set (ptb_set_sobol_table)"); return 1; }
+    k_sobol_points<<<nblk(c->sobol_dim, 256), 256, 0, c->stream>>>(c->d_sobolV, c->sobol_dim, k_first, count, stride, P_dev);
+    c->launches++;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_sobolP(ptb_ctx* c, int nsamp) {
+    if (nsamp > c->sobolP_cap) {
+        if (c->d_sobolP) cudaFree(c->d_sobolP);
+        PTB_CUDA(cudaMalloc(&c->d_sobolP, sizeof(float) * (size_t)nsamp * c->sobol_dim));
+        c->sobolP_cap = nsamp;
+    }
+    return 0;
+}
+
+// bounce loop shared by every engine: extend -> shade -> shadow, up to 5 times (path.py:25)
+template <int ENGINE>
+static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride, FrameMap fm) {
+    TraceScene S = ptb_trace_scene(c);
+    int policy = ptb_effective_policy(c, c->traversal_request);
+    DevCounters* ctr = c->counting ? c->d_counters : nullptr;
+    cudaStream_t st = c->stream;
+    int cur = 0;
+    for (int depth = 1; depth <= 5; depth++) {
+        ptb_stage_begin(c, ST_EXTEND);
+        if (c->counting) k_extend<true><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[cur], c->d_ctrl, policy, ctr);
+        else k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[cur], c->d_ctrl, policy, ctr);
+        ptb_stage_end(c);
+        ptb_stage_begin(c, ST_SHADE);
+        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, rngtab, dim, rng_stride, fm, c->st,
+                                                            c->d_queue[cur], c->d_queue[cur ^ 1], c->d_shadowq, c->d_ctrl);
+        ptb_stage_end(c);
+        c->launches += 2;
+        if (ENGINE == PTB_ENGINE_PATH) {
+            ptb_stage_begin(c, ST_SHADOW);
+            if (c->counting) k_shadow<true><<<c->blocks_shadow, BLK, 0, st>>>(S, c->st, c->d_shadowq, c->d_ctrl, policy, ctr);
+            else k_shadow<false><<<c->blocks_shadow, BLK, 0, st>>>(S, c->st, c->d_shadowq, c->d_ctrl, policy, ctr);
+            ptb_stage_end(c);
+            c->launches++;
+        }
+        k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
+        c->launches++;
+        cur ^= 1;
+    }
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev) {
+    if (c->nx <= 0 || c->ny <= 0) { ptb_set_error("film size not set (ptb_set_size)"); return 1; }
+    if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
+    if (ptb_wf_upload_params(c)) return 1;
+    cudaStream_t st = c->stream;
+    DevCounters* ctr = c->counting ? c->d_counters : nullptr;
+    FrameMap fm = make_frame(c->nx, c->ny);
+
+    if (engine == PTB_ENGINE_MLT) {
+        if (c->mlt_count <= 0) { ptb_set_error("MLT chains not initialised (ptb_mlt_reset)"); return 1; }
+        for (int it = 0; it < count; it++) {
+            int n = c->mlt_count;
+            ptb_stage_begin(c, ST_RAYGEN);
+            k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
+            k_mlt_raygen<<<nblk(n), BLK, 0, st>>>(c->d_params, c->d_Xold, c->d_Xnew, n, c->mlt_first, c->mlt_seed, c->mlt_iter, c->mlt_lsp, c->mlt_sigma,
+                                                  c->st, c->d_queue[0], c->d_ctrl, ctr);
+            ptb_stage_end(c);
+            c->launches += 2;
+            if (run_bounces<PTB_ENGINE_PATH>(c, c->d_Xnew, 0, 32, fm)) return 1;
+            ptb_stage_begin(c, ST_ACCUM);
+            k_mlt_finish<<<nblk(n), BLK, 0, st>>>(c->d_Xold, c->d_Xnew, c->d_Lold, c->st.result, n, c->mlt_first, c->mlt_seed, c->mlt_iter, c->nx, c->ny, c->d_film);
+            ptb_stage_end(c);
+            c->launches++;
+            c->mlt_iter++;
+        }
+        PTB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    int per_batch = (int)(c->max_paths / fm.pps);
+    if (per_batch < 1) { ptb_set_error("film %dx%d needs %d path slots per sample, pool has %lld", c->nx, c->ny, fm.pps, (long long)c->max_paths); return 1; }
+    if (sample_out_dev) count = 1;
+    for (int done = 0; done < count; done += per_batch) {
+        int ns = count - done < per_batch ? count - done : per_batch;
+        if (ensure_sobolP(c, ns)) return 1;
+        ptb_stage_begin(c, ST_RAYGEN);
+        if (ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
+        k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
+        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, c->st, c->d_queue[0], c->d_ctrl, ctr);
+        ptb_stage_end(c);
+        c->launches += 2;
+        if (engine == PTB_ENGINE_PREVIEW) {
+            TraceScene S = ptb_trace_scene(c);
+            int policy = ptb_effective_policy(c, c->traversal_request);
+            ptb_stage_begin(c, ST_EXTEND);
+            k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[0], c->d_ctrl, policy, nullptr);
+            ptb_stage_end(c);
+            ptb_stage_begin(c, ST_ACCUM);
+            size_t pass = (size_t)c->caps.max_filmsize;
+            k_preview<<<nblk(fm.pps), BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, fm, ns, c->st, c->d_film + pass, c->d_film + 2 * pass);
+            ptb_stage_end(c);
+            c->launches += 2;
+            continue;
+        }
+        int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, c->d_sobolP, c->sobol_dim, 0, fm)
+                                           : run_bounces<PTB_ENGINE_BRUTE>(c, c->d_sobolP, c->sobol_dim, 0, fm);
+        if (rc) return 1;
+        ptb_stage_begin(c, ST_ACCUM);
+        k_accumulate<<<nblk(fm.pps), BLK, 0, st>>>(c->d_film, c->st.result, fm, ns, sample_out_dev);
+        ptb_stage_end(c);
+        c->launches++;
+    }
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev) {
+    if (c->nx <= 0 || c->ny <= 0) { ptb_set_error("film size not set (ptb_set_size)"); return 1; }
+    if (ptb_wf_upload_params(c)) return 1;
+    cudaStream_t st = c->stream;
+    FrameMap fm = make_frame(c->nx, c->ny);
+    if (fm.pps > c->max_paths) { ptb_set_error("film larger than the path pool"); return 1; }
+    if (ensure_sobolP(c, 1)) return 1;
+    if (ptb_wf_sobol_points(c, k, 1, 1, c->d_sobolP)) return 1;
+    k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
+    k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, c->st, c->d_queue[0], c->d_ctrl, nullptr);
+    if (rays_dev) k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, rays_dev, nullptr, nullptr, nullptr, nullptr, 0);
+    if (hit_dev || depth_dev || index_dev || uv_dev) {
+        if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
+        TraceScene S = ptb_trace_scene(c);
+        int policy = ptb_effective_policy(c, c->traversal_request);
+        k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[0], c->d_ctrl, policy, nullptr);
+        k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, nullptr, hit_dev, depth_dev, index_dev, uv_dev, 1);
+    }
+    c->launches += 5;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev, const float* dis_dev, int m, int policy, int anyhit,
+                     int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev) {
+    if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
+    TraceScene S = ptb_trace_scene(c);
+    k_intersect_tap<<<nblk(m), BLK, 0, c->stream>>>(S, rays_dev, avoid_dev, dis_dev, m, ptb_effective_policy(c, policy), anyhit, hit_dev, depth_dev, index_dev, uv_dev);
+    c->launches++;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev) {
+    if (ptb_wf_upload_params(c)) return 1;
+    k_shade_tap<<<nblk(m), BLK, 0, c->stream>>>(c->d_params, c->d_texels, what, in0_dev, in1_dev, ini_dev, m, out_dev);
+    c->launches++;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev) {
+    const float4* film = c->d_film + (size_t)pass * c->caps.max_filmsize;
+    k_resolve<<<nblk((long long)c->nx * c->ny), BLK, 0, c->stream>>>(film, c->nx, c->ny, mode, out_dev);
+    c->launches++;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_mlt_reset(ptb_ctx* c) {
+    k_mlt_reset<<<nblk(c->mlt_count), BLK, 0, c->stream>>>(c->d_Xold, c->d_Lold, c->mlt_count, c->mlt_first, c->mlt_seed);
+    c->launches++;
+    c->mlt_iter = 0;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps) {
+    size_t bytes = (size_t)mbytes << 20, n4 = bytes / 16;
+    float4* buf = nullptr; float* sink = nullptr;
+    PTB_CUDA(cudaMalloc(&buf, bytes));
+    PTB_CUDA(cudaMalloc(&sink, 4));
+    PTB_CUDA(cudaMemsetAsync(buf, 0, bytes, c->stream));
+    int grid = c->sm_count * 8;
+    k_l2_read<<<grid, 256, 0, c->stream>>>(buf, n4, 2, sink);   // warm the L2
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    k_l2_read<<<grid, 256, 0, c->stream>>>(buf, n4, iters, sink);
+    cudaEventRecord(b, c->stream);
+    PTB_CUDA(cudaEventSynchronize(b));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    *gbps = (float)((double)bytes * iters / (ms * 1e-3) / 1e9);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    c->launches += 2;
+    return 0;
+}
