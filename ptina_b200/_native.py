@@ -85,7 +85,7 @@ def _ptr(a):
     if a is None:
         return None
     if isinstance(a, np.ndarray):
-        return ctypes.c_void_p(a.ctypes.data)
+        return a.ctypes.data_as(ctypes.c_void_p)     # keeps a reference to `a` for the lifetime of the pointer object
     return ctypes.c_void_p(a.data_ptr())   # torch.Tensor
 
 

@@ -14,6 +14,7 @@ for name in sys.argv[1:] or ['cornell_boxes', 'cornell_monkey', 'matball', 'mega
     nx, ny = sc['size']
     if name != 'mega_small':
         sc['size'] = (128, 128 * ny // nx)
+    ctx.sobol_reset()
     t = time.time(); scenes.apply(worker, sc); t_gpu = time.time() - t
     ref = oracle.Oracle(); scenes.apply(ref, sc)
     info = ctx.tree
