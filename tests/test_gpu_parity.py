@@ -1,0 +1,362 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the PTina-style facade) against the CPU oracle on the same
+seeded inputs.  Bit-exact: Morton codes, sorted (mc, id), child/leaf topology, node boxes, primary rays, primary hit ids /
+depth / uv.  Float: BSDF eval / pdf <= 1e-5 relative, per-sample radiance, accumulated film.  Plus size-independent
+properties at BASELINE.json's full sizes (ordered traversal == the reference's own traversal order, on the GPU)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from ptina_b200 import scenes, worker, _native  # noqa: E402
+
+SMALL = {'cornell_boxes': (96, 96), 'cornell_monkey': (96, 96), 'matball': (96, 96), 'mega_small': (128, 72)}
+
+
+def load(gpu, name, size=None, ref=True):
+    sc = scenes.CONFIGS[name]()
+    if size:
+        sc['size'] = size
+    gpu.sobol_reset()
+    scenes.apply(worker, sc)
+    worker.clear()
+    o = None
+    if ref:
+        o = oracle.Oracle()
+        scenes.apply(o, sc)
+    return sc, o
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+@pytest.mark.parametrize('name', list(SMALL))
+def test_lbvh_bit_exact(gpu, name):
+    sc, o = load(gpu, name, SMALL[name])
+    info = gpu.tree
+    a, b = gpu.export_tree(), o.export_tree()
+    for key in ('mc', 'id', 'leaf', 'child'):
+        assert np.array_equal(a[key], b[key]), f'{name}: {key} differs'
+    for key in ('bmin', 'bmax'):
+        assert np.array_equal(bits(a[key]), bits(b[key])), f'{name}: {key} differs'
+    assert info.valid == 1 and info.depth == o.validate_tree() and info.policy == _native.TRAVERSE_ORDERED
+
+
+@pytest.mark.parametrize('name', list(SMALL))
+def test_primary_rays_and_hits_bit_exact(gpu, name):
+    sc, o = load(gpu, name, SMALL[name])
+    for k in (65, 66, 97, 1088):
+        a, b = gpu.trace_primary(k), o.primary(k)
+        assert np.array_equal(bits(a['rays']), bits(b['rays'])), f'{name} k={k}: primary rays differ'
+        assert np.array_equal(a['index'], b['index']), f'{name} k={k}: {(a["index"] != b["index"]).sum()} hit ids differ'
+        assert np.array_equal(a['hit'], b['hit'])
+        h = b['hit'] == 1
+        assert np.array_equal(bits(a['depth'])[h], bits(b['depth'])[h]) and np.array_equal(bits(a['uv'])[h], bits(b['uv'])[h])
+
+
+def test_sobol_points_bit_exact(gpu):
+    o = oracle.Oracle()
+    for k in (1, 64, 65, 97, 4095, 1 << 19):
+        assert np.array_equal(bits(gpu.sobol_point(k)), bits(o.sobol_point(k)))
+
+
+@pytest.mark.parametrize('name', ['cornell_monkey', 'mega_small'])
+def test_secondary_rays_match_reference_order(gpu, name):
+    """Incoherent rays from random surface points: ordered traversal, the literal traversal on the GPU and the oracle agree
+    on hit id, depth and uv bit for bit; shadow queries agree with `closest depth <= dis`."""
+    sc, o = load(gpu, name, SMALL[name])
+    rng = np.random.default_rng(3)
+    m = 20000
+    verts = np.asarray(sc['vertices'], np.float32)[:, :3].reshape(-1, 3, 3)
+    f = rng.integers(0, verts.shape[0], m)
+    w = rng.dirichlet([1, 1, 1], m).astype(np.float32)
+    org = (verts[f] * w[:, :, None]).sum(1)
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, d], 1).astype(np.float32)
+    avoid = f.astype(np.int32)
+    ref = o.intersect(rays, avoid)
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_REFERENCE):
+        got = gpu.intersect(rays, avoid, policy)
+        assert np.array_equal(got['index'], ref['index']), f'policy {policy}: {(got["index"] != ref["index"]).sum()} ids differ'
+        h = ref['hit'] == 1
+        assert np.array_equal(bits(got['depth'])[h], bits(ref['depth'])[h]) and np.array_equal(bits(got['uv'])[h], bits(ref['uv'])[h])
+    dis = np.where(ref['hit'] == 1, ref['depth'] * rng.choice([0.5, 1.0, 1.5], m), 5.0).astype(np.float32)
+    want = ((ref['hit'] == 1) & (ref['depth'] <= dis)).astype(np.int32)
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_REFERENCE):
+        assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want)
+
+
+def _random_materials(rng, m):
+    p = np.zeros((m, 14), np.float32)
+    p[:, 0:3] = rng.uniform(0.05, 1.0, (m, 3))
+    p[:, 3] = rng.choice([0.0, 0.3, 1.0], m)                  # metallic
+    p[:, 4] = rng.uniform(0.05, 1.0, m)                       # roughness
+    p[:, 5] = rng.uniform(0.0, 1.0, m)                        # specular
+    p[:, 6] = rng.uniform(0.0, 1.0, m)
+    p[:, 7] = rng.choice([0.0, 0.5], m)                       # subsurface
+    p[:, 8] = rng.choice([0.0, 0.7], m)                       # sheen
+    p[:, 9] = rng.uniform(0.0, 1.0, m)
+    p[:, 10] = rng.choice([0.0, 0.0, 1.0], m)                 # clearcoat
+    p[:, 11] = rng.uniform(0.0, 1.0, m)
+    p[:, 12] = rng.choice([0.0, 0.0, 0.5, 1.0], m)            # transmission
+    p[:, 13] = rng.uniform(1.1, 2.0, m)                       # ior
+    return p
+
+
+def _unit(rng, m, upper=None):
+    v = rng.normal(size=(m, 3))
+    if upper is not None:
+        v[:, 2] = np.abs(v[:, 2]) * upper
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def relerr(a, b, floor=1e-6):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def test_bsdf_eval_within_1e5(gpu):
+    rng = np.random.default_rng(11)
+    m = 50000
+    params = _random_materials(rng, m)
+    nrm = _unit(rng, m)
+    wi, wo = _unit(rng, m), _unit(rng, m)
+    flip = (wi * nrm).sum(1) < 0
+    wi[flip] = -wi[flip]                                         # the integrator always passes the facing normal, sign >= 0
+    geom = np.concatenate([nrm, np.ones((m, 1), np.float32), wi, wo], 1)
+    a, b = gpu.eval_bsdf(params, geom), oracle.eval_bsdf(params, geom)
+    assert np.isfinite(b).all()
+    # north_star: per-path BSDF eval within 1e-5 relative (relative to the value's own magnitude; floor for ~0 results)
+    scale = np.maximum(np.abs(b).max(1, keepdims=True), 1e-4)
+    assert (np.abs(a - b) / scale).max() <= 1e-5, (np.abs(a - b) / scale).max()
+
+
+def test_bsdf_sample_within_1e5(gpu):
+    rng = np.random.default_rng(12)
+    m = 50000
+    params = _random_materials(rng, m)
+    params[:, 10] = 0.0                                           # clearcoat sampling is NaN-driven in the reference (sample_GTR1); below
+    nrm = _unit(rng, m)
+    wi = _unit(rng, m)
+    flip = (wi * nrm).sum(1) < 0
+    wi[flip] = -wi[flip]
+    samp = rng.random((m, 3)).astype(np.float32)
+    geom = np.concatenate([nrm, np.ones((m, 1), np.float32), wi, samp], 1)
+    a, b = gpu.sample_bsdf(params, geom), oracle.sample_bsdf(params, geom)
+    assert np.isfinite(b).all()
+    assert np.abs(a[:, :3] - b[:, :3]).max() <= 2e-5                                   # unit directions: absolute
+    assert relerr(a[:, 3], b[:, 3], 1e-4).max() <= 1e-5                               # pdf
+    cs = np.maximum(np.abs(b[:, 4:]).max(1, keepdims=True), 1e-4)
+    assert (np.abs(a[:, 4:] - b[:, 4:]) / cs).max() <= 1e-5                           # colour / throughput factor
+    # every lobe exercised
+    assert (b[:, 3] == 0).any() and np.isclose(b[:, 3], 1 / np.pi).any() and (params[:, 12] > 0).any()
+
+
+def test_clearcoat_lobe_behaves_like_reference(gpu):
+    # microfacet.py:68-71: sqrt(alpha**(2-2u) - 1) is NaN for alpha < 1 -> cosoh = max(0, NaN) = 0 -> invalid sample (zeros)
+    rng = np.random.default_rng(13)
+    m = 4096
+    params = _random_materials(rng, m)
+    params[:, 10] = 1.0
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (m, 1))
+    wi = _unit(rng, m, upper=1.0)
+    samp = rng.random((m, 3)).astype(np.float32)
+    samp[:, 2] *= 0.13                                             # coatrate = lerp(0.04, 0.1, 1) = 0.136 -> coat lobe
+    geom = np.concatenate([nrm, np.ones((m, 1), np.float32), wi, samp], 1)
+    a, b = gpu.sample_bsdf(params, geom), oracle.sample_bsdf(params, geom)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b).any(1)
+    assert np.allclose(a[ok], b[ok], rtol=1e-5, atol=1e-6)
+    assert (b[ok][:, 3] == 0).all()
+
+
+def test_material_fetch_with_textures(gpu):
+    sc, o = load(gpu, 'matball', SMALL['matball'])
+    rng = np.random.default_rng(5)
+    m = 20000
+    mtlid = rng.integers(-1, 4, m).astype(np.int32)
+    uv = rng.uniform(-1.5, 2.5, (m, 2)).astype(np.float32)          # exercises the wrap mode (Python-style %)
+    a, b = gpu.material_get(mtlid, uv), o.material_get(mtlid, uv)
+    assert relerr(a, b, 1e-3).max() <= 1e-5
+
+
+def test_lights_and_world(gpu):
+    sc, o = load(gpu, 'cornell_boxes', SMALL['cornell_boxes'])
+    # add a POINT light as well so both kinds are exercised; order matters for LightPool.hit (first hit wins)
+    from ptina_b200.tools import matrix as mx
+    for api in (worker, o):
+        api.add_light(mx.translate((0.5, 2.0, 0.5)), np.array([3.0, 2.0, 1.0]), 0.3, 'POINT')
+    rng = np.random.default_rng(6)
+    m = 20000
+    org = rng.uniform([-1.9, 0.1, -1.9], [1.9, 3.9, 1.9], (m, 3))
+    rays = np.concatenate([org, _unit(rng, m)], 1).astype(np.float32)
+    a, b = gpu.light_hit(rays), o.light_hit(rays)
+    assert np.array_equal(a[:, 0], b[:, 0]) and (b[:, 0] == 1).sum() > 100
+    assert relerr(a[:, 1:], b[:, 1:], 1e-4).max() <= 1e-5
+    hs = np.concatenate([org, rng.random((m, 3))], 1).astype(np.float32)
+    a, b = gpu.light_sample(hs), o.light_sample(hs)
+    assert relerr(a[:, :5], b[:, :5], 1e-4).max() <= 2e-5
+    assert (np.abs(a[:, 5:] - b[:, 5:]) / np.maximum(np.abs(b[:, 5:]).max(1, keepdims=True), 1e-4)).max() <= 2e-5
+    sc, o = load(gpu, 'matball', SMALL['matball'])
+    d = _unit(rng, m)
+    a, b = gpu.world_at(d), o.world_at(d)
+    # texel lookups near a bilinear cell edge can land on the neighbouring cell (atan2 differs by an ulp): compare robustly
+    bad = relerr(a, b, 1e-3).max(1) > 1e-4
+    assert bad.mean() < 2e-3, bad.mean()
+
+
+@pytest.mark.parametrize('name,engine', [('cornell_boxes', 'path'), ('cornell_monkey', 'path'), ('matball', 'brute'), ('mega_small', 'path')])
+def test_single_sample_radiance(gpu, name, engine):
+    sc, o = load(gpu, name, SMALL[name])
+    ge = {'path': _native.ENGINE_PATH, 'brute': _native.ENGINE_BRUTE}[engine]
+    oe = {'path': oracle.ENGINE_PATH, 'brute': oracle.ENGINE_BRUTE}[engine]
+    for k in (65, 80):
+        a, b = gpu.render_sample(ge, k), o.render_sample(oe, k)
+        assert not np.isnan(a).any()
+        rel = (np.abs(a - b) / np.maximum(np.abs(b).max(2, keepdims=True), 1e-2)).max(2)
+        # libm differences (sin/cos/atan2/pow, <= 2 ulp) occasionally flip a discrete decision deep in a path; those pixels
+        # are isolated.  Everything else agrees to float rounding.
+        assert (rel > 1e-4).mean() < 2e-3, f'{name} k={k}: {(rel > 1e-4).mean():.2e} of pixels differ'
+        assert np.median(rel) < 1e-6
+
+
+@pytest.mark.parametrize('name,engine,spp', [('cornell_boxes', 'path', 32), ('cornell_monkey', 'path', 32), ('matball', 'brute', 32), ('mega_small', 'path', 16)])
+def test_accumulated_film_rel_rmse(gpu, name, engine, spp):
+    """Same Sobol indices on both sides: per-pixel relative RMSE of the accumulated image <= 1e-3 (north_star's gate is stated
+    for converged 1024-spp images; with identical sample sets it already holds at a few spp)."""
+    sc, o = load(gpu, name, SMALL[name])
+    ge = {'path': _native.ENGINE_PATH, 'brute': _native.ENGINE_BRUTE}[engine]
+    oe = {'path': oracle.ENGINE_PATH, 'brute': oracle.ENGINE_BRUTE}[engine]
+    gpu.render(ge, spp)
+    o.render(oe, spp)
+    a, b = worker.get_image(), o.get_image()
+    assert a.shape == b.shape == (*SMALL[name], 4) and np.all(a[..., 3] == 1)
+    fa, fb = gpu.get_film(), o.get_film()
+    assert np.all(fa[..., 3] == spp) and np.all(fb[..., 3] == spp)
+    rmse = np.sqrt((((a[..., :3] - b[..., :3]) / np.maximum(b[..., :3], 1e-2)) ** 2).mean())
+    assert rmse <= 1e-3, rmse
+    out_a, out_b = np.zeros(a.shape[0] * a.shape[1] * 3, np.float32), np.zeros(a.shape[0] * a.shape[1] * 3, np.float32)
+    worker.fast_export_image(out_a); o.fast_export_image(out_b)
+    assert np.array_equal(out_a.reshape(a.shape[1], a.shape[0], 3), a[..., :3].transpose(1, 0, 2))
+    assert gpu.sobol_time == 64 + spp
+
+
+def test_batching_and_ranges_are_equivalent(gpu):
+    """render(n) == n x render(1) == rank-interleaved render_range shards summed (what the multi-GPU path does)."""
+    sc, o = load(gpu, 'cornell_monkey', (64, 64), ref=False)
+    gpu.render(_native.ENGINE_PATH, 6)
+    a = gpu.get_film().copy()
+    gpu.sobol_reset(); worker.clear()
+    for _ in range(6):
+        gpu.render(_native.ENGINE_PATH, 1)
+    b = gpu.get_film().copy()
+    assert np.array_equal(bits(a), bits(b))
+    worker.clear()
+    from ptina_b200.dist import shard_range
+    for rank in range(4):
+        first, count, stride = shard_range(65, 6, rank, 4)
+        gpu.render_range(_native.ENGINE_PATH, first, count, stride)
+    c = gpu.get_film()
+    assert np.allclose(a, c, rtol=1e-5, atol=1e-6) and np.array_equal(a[..., 3], c[..., 3])
+
+
+def test_full_size_ordered_equals_reference_order(gpu):
+    """BASELINE configs 1/2 at full 512x512: hit ids / depth / uv of the optimised traversal equal the literal reference
+    traversal run on the GPU, for primary rays of several Sobol points (size-independent property)."""
+    for name in ('cornell_boxes', 'cornell_monkey'):
+        sc, _ = load(gpu, name, ref=False)
+        for k in (66, 97):
+            gpu.set_traversal(_native.TRAVERSE_ORDERED)
+            a = gpu.trace_primary(k)
+            gpu.set_traversal(_native.TRAVERSE_REFERENCE)
+            b = gpu.trace_primary(k)
+            gpu.set_traversal(_native.TRAVERSE_AUTO)
+            assert np.array_equal(a['index'], b['index']) and np.array_equal(bits(a['depth']), bits(b['depth'])) and np.array_equal(bits(a['uv']), bits(b['uv']))
+        # and the whole path tracer: film from the ordered policy == film from the literal policy
+        gpu.set_traversal(_native.TRAVERSE_ORDERED); gpu.sobol_reset(); worker.clear(); gpu.render(_native.ENGINE_PATH, 2); fa = gpu.get_film().copy()
+        gpu.set_traversal(_native.TRAVERSE_REFERENCE); gpu.sobol_reset(); worker.clear(); gpu.render(_native.ENGINE_PATH, 2); fb = gpu.get_film().copy()
+        gpu.set_traversal(_native.TRAVERSE_AUTO)
+        assert np.array_equal(bits(fa), bits(fb)), f'{name}: {(bits(fa) != bits(fb)).sum()} film words differ between traversal policies'
+
+
+def test_mega_scene_full_size(gpu):
+    """Config 4 (~1M triangles, 1920x1080): tree is a valid Karras tree within the 32-entry stack, Morton codes sorted, and the
+    optimised traversal equals the literal one on the GPU for every primary ray and for a full path-traced sample."""
+    sc, _ = load(gpu, 'mega', ref=False)
+    info = gpu.tree
+    assert info.n == len(sc['mtlids']) > 1_000_000 and info.valid == 1 and info.depth <= 31
+    t = gpu.export_tree()
+    assert (np.diff(t['mc']) >= 0).all() and np.array_equal(np.sort(t['id']), np.arange(info.n))
+    assert np.array_equal(t['leaf'], t['id'])
+    pos = np.asarray(sc['vertices'], np.float32)[:, :3]
+    assert np.array_equal(t['bmin'][0], pos.min(0)) and np.array_equal(t['bmax'][0], pos.max(0))
+    gpu.set_traversal(_native.TRAVERSE_ORDERED); a = gpu.trace_primary(65)
+    gpu.set_traversal(_native.TRAVERSE_REFERENCE); b = gpu.trace_primary(65)
+    assert np.array_equal(a['index'], b['index']) and np.array_equal(bits(a['depth']), bits(b['depth'])) and np.array_equal(bits(a['uv']), bits(b['uv']))
+    assert (a['hit'] == 1).mean() > 0.5
+    gpu.set_traversal(_native.TRAVERSE_ORDERED); sa = gpu.render_sample(_native.ENGINE_PATH, 65)
+    gpu.set_traversal(_native.TRAVERSE_REFERENCE); sb = gpu.render_sample(_native.ENGINE_PATH, 65)
+    gpu.set_traversal(_native.TRAVERSE_AUTO)
+    assert np.array_equal(bits(sa), bits(sb))
+
+
+def test_edge_cases_and_errors(gpu):
+    from ptina_b200.model import ModelPool
+    from ptina_b200.tree import BVHTree
+    sc, _ = load(gpu, 'cornell_boxes', (32, 32), ref=False)
+    # stale tree is refused, not silently used
+    ModelPool().load(sc['vertices'][:30], sc['mtlids'][:10])
+    with pytest.raises(_native.NativeError, match='stale'):
+        gpu.render(_native.ENGINE_PATH, 1)
+    BVHTree().build()
+    gpu.render(_native.ENGINE_PATH, 1)
+    # default material (mtlid None -> -1) and float64 input
+    ModelPool().load(np.asarray(sc['vertices'], np.float64))
+    BVHTree().build()
+    o = oracle.Oracle(); scenes.apply(o, dict(sc, mtlids=-np.ones(len(sc['mtlids']), np.int32)))
+    a, b = gpu.render_sample(_native.ENGINE_PATH, 70), o.render_sample(oracle.ENGINE_PATH, 70)
+    assert np.median(np.abs(a - b)) < 1e-6
+    # two triangles: smallest real tree
+    ModelPool().load(sc['vertices'][:6], sc['mtlids'][:2]); BVHTree().build()
+    assert gpu.tree.valid == 1 and gpu.tree.depth == 2
+    o = oracle.Oracle(); scenes.apply(o, dict(sc, vertices=sc['vertices'][:6], mtlids=sc['mtlids'][:2]))
+    assert np.array_equal(gpu.trace_primary(65)['index'], o.primary(65)['index'])
+    # capacity errors keep the reference's messages
+    with pytest.raises(AssertionError, match='too many faces'):
+        ModelPool().load(np.zeros((3 * 2**21, 8), np.float32))
+    with pytest.raises(_native.NativeError, match='exceeds max_filmsize'):
+        gpu.set_size(2048, 2048)
+    from ptina_b200.image import ImagePool
+    with pytest.raises(RuntimeError, match='Out of memory!'):
+        ImagePool().load([np.zeros((2048, 2049), np.float32)])
+    # duplicate-heavy geometry (coincident triangles -> runs of equal Morton codes): the reference's tree is not a proper tree;
+    # the library must notice, fall back to the reference's traversal order, and still agree with the oracle
+    v = np.tile(np.asarray(sc['vertices'][:3], np.float32), (9, 1)); v[3 * 4:3 * 5, :3] += 0.5
+    for api in (worker, ):
+        ModelPool().load(v, np.zeros(9, np.int32)); BVHTree().build()
+    o = oracle.Oracle(); scenes.apply(o, dict(sc, vertices=v, mtlids=np.zeros(9, np.int32)))
+    ta, tb = gpu.export_tree(), o.export_tree()
+    assert np.array_equal(ta['child'], tb['child']) and np.array_equal(ta['mc'], tb['mc'])
+    if o.validate_tree() < 0:
+        assert gpu.tree.valid == 0 and gpu.tree.policy == _native.TRAVERSE_REFERENCE
+    assert np.array_equal(gpu.trace_primary(65)['index'], o.primary(65)['index'])
+    load(gpu, 'cornell_boxes', (32, 32), ref=False)
+
+
+def test_preview_engine_passes(gpu):
+    sc, o = load(gpu, 'cornell_monkey', (64, 64))
+    from ptina_b200.engine import PreviewEngine
+    PreviewEngine().render(2)
+    alb, nrm = worker.get_image(1), worker.get_image(2)
+    prim = o.primary(65)
+    hit = prim['hit'].reshape(64, 64) == 1
+    assert np.all(alb[..., 3] == 1) and np.all(nrm[..., 3] == 1)
+    assert np.allclose(np.linalg.norm(nrm[hit][:, :3], axis=1), 1, atol=0.2)     # mean of two unit normals
+    assert np.all(alb[~hit][:, :3] == 0) and (alb[hit][:, :3].max(1) > 0).all()
+    assert np.allclose(worker.get_image(0), [0.9, 0.4, 0.9, 0.0])                  # pass 0 untouched -> magenta
+
+
+def test_native_library_is_what_ran(gpu, native_so):
+    maps = open('/proc/self/maps').read()
+    assert 'libptina_b200.so' in maps
+    assert gpu.launches() > 0
