@@ -290,7 +290,30 @@ def metropolis(nx=512, ny=512):
     return s
 
 
-CONFIGS = {'cornell_boxes': cornell_boxes, 'cornell_monkey': cornell_monkey, 'matball': matball, 'mega': mega,
+
+def mini_matball():
+    """Golden-fixture scene (tests/golden): a small cousin of config 3: glass / metal / textured UV spheres (8x6 -> 80 triangles each) on a ground quad, 16x16 checker,
+    32x16 environment map -- sized for the Python interpreter."""
+    sp = uvsphere(8, 6, 1.0)
+    mats = [material((0.7, 0.7, 0.7), roughness=0.6),
+            material((0.95, 0.98, 1.0), roughness=0.1, transmission=1.0, ior=1.45),
+            material((0.95, 0.75, 0.35), metallic=1.0, roughness=0.25),
+            material((1.0, 1.0, 1.0), roughness=0.5, tex={'basecolor': 0}),
+            material((0.3, 0.5, 0.9), roughness=0.4, clearcoat=1.0, sheen=0.5, subsurface=0.3, transmission=0.5)]
+    g = quad((-6, 0, 6), (6, 0, 6), (6, 0, -6), (-6, 0, -6))
+    prims = [(*g, np.identity(4), 0), (*sp, mx.translate((-2.3, 1.0, 0.0)), 1), (*sp, mx.translate((0.0, 1.0, 0.0)), 2),
+             (*sp, mx.translate((2.3, 1.0, 0.0)) @ mx.eularXYZ((0.3, 0.4, 0.0)), 3), (*sp, mx.translate((0.0, 1.0, 2.2)) @ mx.scale(0.6), 4)]
+    v, m = compose_multiple_meshes(prims)
+    pers = mx.perspective(fov=45, aspect=1) @ mx.lookat(pos=(0, 0.9, 0), back=(0, 2.2, 8.0))
+    chk = _checker(16, 4)
+    env = _envmap(32, 16)
+    return dict(name='mini_matball', vertices=v, mtlids=m.astype(np.int32), materials=mats, images=[chk, env],
+                lights=[(mx.translate((1.0, 4.0, 2.0)), np.array([30.0, 28.0, 25.0]), 0.4, 'POINT')],
+                world_light=([1.0] * 4, 1), pers=pers, size=(12, 12), engine='brute', spp=2)
+
+
+
+CONFIGS = {'mini_matball': mini_matball, 'cornell_boxes': cornell_boxes, 'cornell_monkey': cornell_monkey, 'matball': matball, 'mega': mega,
            'mega_small': mega_small, 'metropolis': metropolis}
 
 
