@@ -161,6 +161,9 @@ int ptb_reset_counters(ptb_ctx* ctx);
 int ptb_get_stage_ms(ptb_ctx* ctx, float ms[5]);
 /* kernels launched by this context since the last ptb_reset_counters */
 int ptb_get_launches(ptb_ctx* ctx, int64_t* n);
+/* device self-test of the exact-division shortcut used by the traversal: compares div_exact(a, d, RN(1/d)) with the
+ * IEEE quotient a / d bit for bit on n random operand pairs (what = 0: slab-test ranges, 1: wide ranges); *fails = mismatches */
+int ptb_selftest(ptb_ctx* ctx, int what, int64_t n, uint64_t seed, int64_t* fails);
 /* measured L2-resident read bandwidth (GB/s): streams a `mbytes` buffer `iters` times with 16-B loads */
 int ptb_measure_l2(ptb_ctx* ctx, int mbytes, int iters, float* gbps);
 

@@ -49,7 +49,7 @@ SYMBOLS = [
     'ptb_film_ptr', 'ptb_render', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_get_image',
     'ptb_fast_export_image', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
     'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_render_sample',
-    'ptb_set_counting', 'ptb_get_counters', 'ptb_reset_counters', 'ptb_get_stage_ms', 'ptb_get_launches', 'ptb_measure_l2',
+    'ptb_set_counting', 'ptb_get_counters', 'ptb_reset_counters', 'ptb_get_stage_ms', 'ptb_get_launches', 'ptb_measure_l2', 'ptb_selftest',
 ]
 
 _lib = None
@@ -371,6 +371,11 @@ class Context:
         n = ctypes.c_int64()
         self._check(self.L.ptb_get_launches(self.h, ctypes.byref(n)))
         return n.value
+
+    def selftest(self, what=0, n=1 << 28, seed=1):
+        f = ctypes.c_int64()
+        self._check(self.L.ptb_selftest(self.h, int(what), ctypes.c_int64(n), ctypes.c_uint64(seed), ctypes.byref(f)))
+        return f.value
 
     def measure_l2(self, mbytes=64, iters=20):
         g = ctypes.c_float()

@@ -13,7 +13,7 @@ void ptb_set_error(const char* fmt, ...) {
 
 TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
-    S.nodes = c->d_nodes; S.tris = c->d_tris; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
+    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
     for (int k = 0; k < 3; k++) { S.root_lo[k] = c->root_lo[k]; S.root_hi[k] = c->root_hi[k]; }
     return S;
 }
@@ -110,7 +110,7 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
         dmalloc(&c->d_mc, nf) || dmalloc(&c->d_id, nf) || dmalloc(&c->d_mc_tmp, nf) || dmalloc(&c->d_id_tmp, nf) || dmalloc(&c->d_leaf, nf) ||
         dmalloc(&c->d_child, nf) || dmalloc(&c->d_bmin, nf * 3) || dmalloc(&c->d_bmax, nf * 3) || dmalloc(&c->d_ready, nf) ||
         dmalloc(&c->d_parentcnt, nf * 2) || dmalloc(&c->d_range, nf) || dmalloc(&c->d_height, nf) || dmalloc(&c->d_nodes, nf) ||
-        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
+        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_slot_of, nf) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
         delete c; return 1;
     }
     PTB_CUDA(cudaMemset(c->d_film, 0, sizeof(float4) * (size_t)d.max_filmsize * d.max_filmpasses));
@@ -133,7 +133,7 @@ int ptb_destroy(ptb_ctx* c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
-                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_sort_tmp, c->d_scalars,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_slot_of, c->d_sort_tmp, c->d_scalars,
                     c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->st.sh_d, c->st.sh_c, c->d_queue[0], c->d_queue[1], c->d_shadowq,
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -423,6 +423,14 @@ int ptb_get_stage_ms(ptb_ctx* c, float ms[5]) {
     return 0;
 }
 int ptb_get_launches(ptb_ctx* c, int64_t* n) { CHECK_CTX(c); *n = c->launches; return 0; }
+int ptb_selftest(ptb_ctx* c, int what, int64_t n, uint64_t seed, int64_t* fails) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    long long f = 0;
+    int rc = ptb_wf_selftest(c, what, (long long)n, (unsigned long long)seed, &f);
+    *fails = f;
+    return rc;
+}
 int ptb_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps) {
     CHECK_CTX(c);
     DeviceGuard g(c->device);

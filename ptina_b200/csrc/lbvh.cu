@@ -227,20 +227,23 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const float* __restrict__ ve
     nodes[i] = N;
 }
 
-// packed 64-byte triangle by leaf slot; u, v, n, uu, uv, vv are the f32 expressions of geometries.py:121-137
-__global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ verts, const int* __restrict__ leaf, int n, Tri64* tris) {
+// packed 64-byte triangle by leaf slot; u, v, n, uu, uv, vv, D are the f32 expressions of geometries.py:121-141
+__global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ verts, const int* __restrict__ leaf, int n, Tri64* tris, int* slot_of) {
     int s = blockIdx.x * BLK + threadIdx.x;
     if (s >= n) return;
     int f = leaf[s];
     V3 v0 = face_vertex(verts, f, 0), v1 = face_vertex(verts, f, 1), v2 = face_vertex(verts, f, 2);
     V3 u = v1 - v0, v = v2 - v0;
     V3 nrm = cross(u, v);
+    float uu = dot(u, u), uv = dot(u, v), vv = dot(v, v);
+    float D = uv * uv - uu * vv;
     Tri64 T;
-    T.a = make_float4(v0.x, v0.y, v0.z, __int_as_float(f));
-    T.b = make_float4(u.x, u.y, u.z, dot(u, u));
-    T.c = make_float4(v.x, v.y, v.z, dot(u, v));
-    T.d = make_float4(nrm.x, nrm.y, nrm.z, dot(v, v));
+    T.a = make_float4(v0.x, v0.y, v0.z, 1.0f / D);
+    T.b = make_float4(u.x, u.y, u.z, uu);
+    T.c = make_float4(v.x, v.y, v.z, uv);
+    T.d = make_float4(nrm.x, nrm.y, nrm.z, vv);
     tris[s] = T;
+    slot_of[f] = s;      // leaf[] is a permutation of the faces, so this is its inverse
 }
 
 inline int nblk(int n) { return (n + BLK - 1) / BLK; }
@@ -307,7 +310,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
         k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, c->d_bmin, c->d_bmax, n, c->d_nodes);
         c->launches += 2;
     }
-    if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris); c->launches++; }
+    if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }
     PTB_CUDA(cudaEventRecord(e1, st));
     {
         int h_scal[16];

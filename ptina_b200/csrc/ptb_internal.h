@@ -83,6 +83,7 @@ struct ptb_ctx {
     int32_t* d_height = nullptr;
     Node64* d_nodes = nullptr;
     Tri64* d_tris = nullptr;
+    int32_t* d_slot_of = nullptr;   // face id -> leaf slot
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)
     ptb_tree_info tree_info{};
@@ -132,6 +133,7 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
 int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
 int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev);
 int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
+int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails);
 int ptb_wf_mlt_reset(ptb_ctx* c);
 void ptb_stage_begin(ptb_ctx* c, int stage);
 void ptb_stage_end(ptb_ctx* c);

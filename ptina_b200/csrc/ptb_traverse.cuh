@@ -17,16 +17,20 @@
 
 // 64-byte packed internal node: both children's boxes and ids in four 16-byte loads.
 //   a = (lo0.xyz, c0)  b = (hi0.xyz, c1)  c = (lo1.xyz, -)  d = (hi1.xyz, -)
-// child id < n : leaf slot (box = that triangle's bounds, used for ordering/culling only -- the reference
-// does not box-test leaves);  id >= n : internal node id-n.
+// child id < n : leaf slot (box = that triangle's bounds; unused by the predicates -- the reference does not box-test
+// leaves);  id >= n : internal node id-n.
 struct __align__(16) Node64 { float4 a, b, c, d; };
 // 64-byte packed triangle, indexed by sorted leaf slot:
-//   a = (v0.xyz, face id)  b = (u.xyz, uu)  c = (v.xyz, uv)  d = (n.xyz, vv)     u=v1-v0, v=v2-v0, n=u x v
+//   a = (v0.xyz, 1/D)  b = (u.xyz, uu)  c = (v.xyz, uv)  d = (n.xyz, vv)     u=v1-v0, v=v2-v0, n=u x v, D = uv*uv - uu*vv
+// Every field is the f32 expression geometries.py:121-141 evaluates per test (they depend on the triangle only), so
+// precomputing them changes no bit; 1/D is the correctly rounded reciprocal used by div_exact below.
 struct __align__(16) Tri64 { float4 a, b, c, d; };
 
 struct TraceScene {
     const Node64* __restrict__ nodes;    // [n-1]
     const Tri64* __restrict__ tris;      // [n]  by leaf slot
+    const int* __restrict__ leaf;        // [n]  slot -> face id      (lbvh.py:55)
+    const int* __restrict__ slot_of;     // [n]  face id -> slot      (inverse of leaf, proper trees only)
     // reference arrays (lbvh.py:50-59) for the literal traversal
     const float* __restrict__ bmin;      // [n-1][3]
     const float* __restrict__ bmax;      // [n-1][3]
@@ -71,8 +75,42 @@ PTB_D bool slab_ref(float lox, float loy, float loz, float hix, float hiy, float
     return hit;
 }
 
-// geometries.py:117-148 on the packed record (u, v, n, uu, uv, vv are the same f32 expressions the
-// reference evaluates per test; D is recomputed).  Returns hit; depth/s/t as the reference.
+// Correctly rounded a / d from the correctly rounded reciprocal r = RN(1/d): two Markstein correction steps.
+// q0 = RN(a*r) is within ~2 ulp; after one step the estimate is faithful, after the second it is RN(a/d) (Markstein's
+// theorem: faithful q, exact residual via FMA, correctly rounded reciprocal).  5 FMA-pipe instructions instead of the
+// ~12 + MUFU of a full IEEE division.  Exactness vs `a / d` is checked on the device over 2^30 operand pairs
+// (ptb_selftest, tests/test_gpu_parity.py) -- operands in the denormal range are outside the guarantee.
+PTB_D float div_exact(float a, float d, float r) {
+    float q = a * r;
+    float e = __fmaf_rn(-q, d, a);
+    q = __fmaf_rn(e, r, q);
+    e = __fmaf_rn(-q, d, a);
+    return __fmaf_rn(e, r, q);
+}
+
+// per-ray constants of the fast slab test
+struct RayPre { V3 o, d, r; bool par; };
+PTB_D RayPre ray_pre(V3 o, V3 d) {
+    RayPre P; P.o = o; P.d = d;
+    P.r = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    P.par = fabsf(d.x) < PTB_EPS || fabsf(d.y) < PTB_EPS || fabsf(d.z) < PTB_EPS;
+    return P;
+}
+// Same boolean and same tnear as slab_ref (identical quotients; min/max instead of the swap; the per-axis early
+// `near > far` checks are implied by the final one because near only grows and far only shrinks).  Rays with an
+// axis-parallel component (|d| < 1e-6) take the literal routine.
+PTB_D bool slab_fast(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayPre& P, float* near_out) {
+    if (P.par) return slab_ref(lox, loy, loz, hix, hiy, hiz, P.o, P.d, near_out);
+    float x1 = div_exact(lox - P.o.x, P.d.x, P.r.x), x2 = div_exact(hix - P.o.x, P.d.x, P.r.x);
+    float y1 = div_exact(loy - P.o.y, P.d.y, P.r.y), y2 = div_exact(hiy - P.o.y, P.d.y, P.r.y);
+    float z1 = div_exact(loz - P.o.z, P.d.z, P.r.z), z2 = div_exact(hiz - P.o.z, P.d.z, P.r.z);
+    float tnear = fmaxf(fmaxf(0.0f, fminf(x1, x2)), fmaxf(fminf(y1, y2), fminf(z1, z2)));
+    float tfar = fminf(fminf(PTB_INF, fmaxf(x1, x2)), fminf(fmaxf(y1, y2), fmaxf(z1, z2)));
+    *near_out = tnear;
+    return !(tnear > tfar);
+}
+
+// geometries.py:117-148 on the packed record, literal (true divisions).  Returns hit; depth/s/t as the reference.
 PTB_D bool tri_ref(const Tri64& T, V3 ro, V3 rd, float* depth, float* s_out, float* t_out) {
     V3 v0 = mk3(T.a.x, T.a.y, T.a.z), u = mk3(T.b.x, T.b.y, T.b.z), v = mk3(T.c.x, T.c.y, T.c.z), nrm = mk3(T.d.x, T.d.y, T.d.z);
     float b = dot(nrm, rd);
@@ -92,6 +130,26 @@ PTB_D bool tri_ref(const Tri64& T, V3 ro, V3 rd, float* depth, float* s_out, flo
     return (0.0f <= s && s <= 1.0f) && (0.0f <= t && s + t <= 1.0f);
 }
 
+// The same test with (i) the depth compared against `tlimit` BEFORE the barycentrics are computed (a candidate with
+// depth > tlimit can never be accepted, so skipping the rest changes nothing) and (ii) s, t through div_exact.
+PTB_D bool tri_fast(const Tri64& T, V3 ro, V3 rd, float tlimit, float* depth, float* s_out, float* t_out) {
+    V3 v0 = mk3(T.a.x, T.a.y, T.a.z), nrm = mk3(T.d.x, T.d.y, T.d.z);
+    float b = dot(nrm, rd);
+    if (!(fabsf(b) >= PTB_EPS)) return false;
+    float a = -dot(nrm, ro - v0);
+    float r = a / b;
+    if (!(r > 0.0f) || r > tlimit) return false;
+    V3 u = mk3(T.b.x, T.b.y, T.b.z), v = mk3(T.c.x, T.c.y, T.c.z);
+    float uu = T.b.w, uv = T.c.w, vv = T.d.w, rD = T.a.w;
+    V3 w = (ro + r * rd) - v0;
+    float wu = dot(w, u), wv = dot(w, v);
+    float D = uv * uv - uu * vv;
+    float s = div_exact(uv * wv - vv * wu, D, rD);
+    float t = div_exact(uv * wu - uu * wv, D, rD);
+    *s_out = s; *t_out = t; *depth = r;
+    return (0.0f <= s && s <= 1.0f) && (0.0f <= t && s + t <= 1.0f);
+}
+
 // ---- tree/lbvh.py:313-347, literal order ------------------------------------------------------------------
 template <bool COUNT>
 PTB_D HitRec trace_reference(const TraceScene& S, V3 ro, V3 rd, int avoid, TraceCounters* C) {
@@ -104,9 +162,9 @@ PTB_D HitRec trace_reference(const TraceScene& S, V3 ro, V3 rd, int avoid, Trace
     while (ntimes < n && sp != 0) {
         int curr = stack[--sp];
         if (curr < n) {
-            Tri64 T = S.tris[curr];
-            int index = __float_as_int(T.a.w);
+            int index = S.leaf[curr];
             if (index != avoid) {
+                const Tri64 T = S.tris[curr];
                 if (COUNT) C->tris++;
                 float dep, s, t;
                 if (tri_ref(T, ro, rd, &dep, &s, &t) && dep < ret.depth) {
@@ -128,9 +186,10 @@ PTB_D HitRec trace_reference(const TraceScene& S, V3 ro, V3 rd, int avoid, Trace
     return ret;
 }
 
-// ---- ordered traversal over packed nodes -----------------------------------------------------------------------
-// ANYHIT: stop at the first accepted triangle with depth <= tmax (shadow rays: the reference calls the
-// ray occluded iff its CLOSEST hit has depth <= dis, which holds iff ANY reachable triangle has).
+// ---- ordered traversal over packed nodes ("while-while": all lanes of a warp run node steps together, then the
+// pending leaves together) ---------------------------------------------------------------------------------------
+// ANYHIT: stop at the first accepted triangle with depth <= tmax (shadow rays: the reference calls the ray occluded
+// iff its CLOSEST hit has depth <= dis, which holds iff ANY reachable triangle has one).
 template <bool ANYHIT, bool COUNT>
 PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float tmax, TraceCounters* C) {
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
@@ -139,69 +198,71 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
         if (n == 1) return trace_reference<COUNT>(S, ro, rd, avoid, C);
         return ret;
     }
-    float limit = ANYHIT ? tmax : PTB_INF;             // distances beyond `limit` cannot change the answer
-    float cull = limit + limit * PTB_CULL_GUARD;
+    const RayPre P = ray_pre(ro, rd);
     {   // the root's own box (the reference pops and tests it first)
         float nr;
         if (COUNT) C->boxes++;
-        if (!slab_ref(S.root_lo[0], S.root_lo[1], S.root_lo[2], S.root_hi[0], S.root_hi[1], S.root_hi[2], ro, rd, &nr)) return ret;
+        if (!slab_fast(S.root_lo[0], S.root_lo[1], S.root_lo[2], S.root_hi[0], S.root_hi[1], S.root_hi[2], P, &nr)) return ret;
     }
+    const int avoid_slot = avoid >= 0 ? S.slot_of[avoid] : -1;
+    // a triangle is accepted iff depth < best (ties: larger slot wins, = the leaf the reference visits first); sub-trees
+    // entered beyond `cull` = best * (1 + 2^-12) are skipped
+    float best = ANYHIT ? fminf(tmax, PTB_INF) : PTB_INF;
+    float cull = best + best * PTB_CULL_GUARD;
     int stack_id[PTB_STACK];
     float stack_near[PTB_STACK];
     int sp = 0;
-    int cur = 0;   // internal node index
+    int cur = 0;          // internal node index, -1 = none
+    float cur_near = 0.0f;
     while (true) {
-        const Node64 N = S.nodes[cur];
-        if (COUNT) C->nodes++;
-        int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
-        float n0, n1;
-        bool h0 = slab_ref(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, ro, rd, &n0);
-        bool h1 = slab_ref(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, ro, rd, &n1);
-        if (COUNT) C->boxes += 2;
-        bool leaf0 = c0 < n, leaf1 = c1 < n;
-        // leaves: always tested when reached (no box predicate in the reference); internal: exact predicate,
-        // then distance culling with a guard band
-        bool go0 = leaf0 ? true : (h0 && !(n0 > cull));
-        bool go1 = leaf1 ? true : (h1 && !(n1 > cull));
+        int pend0 = -1, pend1 = -1;
+        while (cur >= 0) {
+            if (cur_near > cull) { cur = -1; break; }
+            const Node64 N = S.nodes[cur];
+            if (COUNT) C->nodes++;
+            const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
+            const bool leaf0 = c0 < n, leaf1 = c1 < n;
+            float n0 = 0.0f, n1 = 0.0f;
+            bool d0 = false, d1 = false;
+            if (!leaf0) { d0 = slab_fast(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, P, &n0) && !(n0 > cull); if (COUNT) C->boxes++; }
+            if (!leaf1) { d1 = slab_fast(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, P, &n1) && !(n1 > cull); if (COUNT) C->boxes++; }
+            if (leaf0 && c0 != avoid_slot) pend0 = c0;
+            if (leaf1 && c1 != avoid_slot) { if (pend0 < 0) pend0 = c1; else pend1 = c1; }
+            if (d0 && d1) {
+                // nearer first; on equal entry distance child1 first, like the reference
+                const bool first1 = !(n0 < n1);
+                if (sp < PTB_STACK) { stack_id[sp] = (first1 ? c0 : c1) - n; stack_near[sp] = first1 ? n0 : n1; sp++; }
+                if (COUNT) C->max_stack = max(C->max_stack, (unsigned)sp);
+                cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
+            } else if (d0) { cur = c0 - n; cur_near = n0; }
+            else if (d1) { cur = c1 - n; cur_near = n1; }
+            else cur = -1;
+            if (pend0 >= 0) break;
+        }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            bool isleaf = k == 0 ? leaf0 : leaf1;
-            if (!isleaf) continue;
-            int slot = k == 0 ? c0 : c1;
+            const int slot = k == 0 ? pend0 : pend1;
+            if (slot < 0) continue;
             const Tri64 T = S.tris[slot];
-            int index = __float_as_int(T.a.w);
-            if (index == avoid) continue;
             if (COUNT) C->tris++;
             float dep, s, t;
-            if (tri_ref(T, ro, rd, &dep, &s, &t)) {
+            if (tri_fast(T, ro, rd, best, &dep, &s, &t)) {
                 if (ANYHIT) {
-                    if (dep <= tmax) { ret.hit = 1; ret.depth = dep; ret.index = index; ret.u = s; ret.v = t; ret.slot = slot; return ret; }
-                } else if (dep < ret.depth || (dep == ret.depth && ret.hit && slot > ret.slot)) {
-                    ret.depth = dep; ret.index = index; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
-                    cull = dep + dep * PTB_CULL_GUARD;
+                    if (dep < PTB_INF) { ret.hit = 1; ret.depth = dep; ret.u = s; ret.v = t; ret.slot = slot; ret.index = S.leaf[slot]; return ret; }
+                } else if (dep < ret.depth || (ret.hit && slot > ret.slot)) {     // here dep <= best == ret.depth
+                    ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
+                    best = dep; cull = dep + dep * PTB_CULL_GUARD;
                 }
             }
         }
-        bool d0 = go0 && !leaf0 && !(n0 > cull), d1 = go1 && !leaf1 && !(n1 > cull);
-        if (d0 && d1) {
-            // nearer first; on equal entry distance take child1 first like the reference
-            bool first1 = !(n0 < n1);
-            int nearc = first1 ? c1 : c0, farc = first1 ? c0 : c1;
-            float farn = first1 ? n0 : n1;
-            if (sp < PTB_STACK) { stack_id[sp] = farc - n; stack_near[sp] = farn; sp++; }
-            if (COUNT) C->max_stack = max(C->max_stack, (unsigned)sp);
-            cur = nearc - n;
-            continue;
+        if (cur < 0) {
+            while (sp > 0) {
+                --sp;
+                if (!(stack_near[sp] > cull)) { cur = stack_id[sp]; cur_near = stack_near[sp]; break; }
+            }
+            if (cur < 0) break;
         }
-        if (d0) { cur = c0 - n; continue; }
-        if (d1) { cur = c1 - n; continue; }
-        // pop
-        bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (!(stack_near[sp] > cull)) { cur = stack_id[sp]; found = true; break; }
-        }
-        if (!found) break;
     }
+    if (!ANYHIT && ret.hit) ret.index = S.leaf[ret.slot];
     return ret;
 }

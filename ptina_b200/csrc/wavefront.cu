@@ -551,6 +551,31 @@ __global__ void __launch_bounds__(BLK) k_mlt_finish(float* __restrict__ Xold, co
     }
 }
 
+// div_exact(a, d, RN(1/d)) == a / d ?  Operands drawn from a counter-based hash; what = 0: |d| in [1e-6, 1] and |a| up to
+// 1e7 (the slab test's ranges), what = 1: both over [1e-18, 1e18].
+PTB_D float rand_float(uint32_t h, float lo_exp, float hi_exp) {
+    float u = (float)(h >> 9) * (1.0f / 8388608.0f);                  // [0,1)
+    float e = lo_exp + (hi_exp - lo_exp) * u;
+    float m = 1.0f + (float)(wanghash((int)h) & 0x7FFFFF) * (1.0f / 8388608.0f);
+    float v = exp2f(floorf(e)) * m;
+    return (h & 1u) ? -v : v;
+}
+__global__ void __launch_bounds__(256) k_selftest_div(int what, long long n, unsigned long long seed, unsigned long long* fails) {
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        uint32_t h1 = (uint32_t)wanghash((int)(i * 2654435761u + seed)), h2 = (uint32_t)wanghash((int)(h1 ^ (uint32_t)(i >> 32) ^ 0x9E3779B9u));
+        float d = what == 0 ? rand_float(h1, -20.0f, 0.0f) : rand_float(h1, -60.0f, 60.0f);
+        float a = what == 0 ? rand_float(h2, -40.0f, 24.0f) : rand_float(h2, -60.0f, 60.0f);
+        if ((h2 & 0xFF0u) == 0) a = 0.0f;                             // exact zeros are common (origin on a box plane)
+        float q = a / d;
+        float r = 1.0f / d;
+        float f = div_exact(a, d, r);
+        if (__float_as_int(q) != __float_as_int(f) && fabsf(q) > 1e-30f) bad++;
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(fails, bad);
+}
+
 inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 
 }  // namespace
@@ -782,6 +807,20 @@ int ptb_wf_mlt_reset(ptb_ctx* c) {
     c->launches++;
     c->mlt_iter = 0;
     PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails) {
+    unsigned long long* d = nullptr;
+    PTB_CUDA(cudaMalloc(&d, 8));
+    PTB_CUDA(cudaMemsetAsync(d, 0, 8, c->stream));
+    k_selftest_div<<<c->sm_count * 8, 256, 0, c->stream>>>(what, n, seed, d);
+    c->launches++;
+    unsigned long long h = 0;
+    PTB_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    *fails = (long long)h;
     return 0;
 }
 

@@ -377,3 +377,10 @@ def test_native_library_is_what_ran(gpu, native_so):
     maps = open('/proc/self/maps').read()
     assert 'libptina_b200.so' in maps
     assert gpu.launches() > 0
+
+
+def test_exact_division_shortcut(gpu):
+    """div_exact(a, d, RN(1/d)) -- the 5-FMA quotient the slab and barycentric tests use -- equals the IEEE quotient a / d bit for
+    bit on 2^30 operand pairs in the slab test's ranges and 2^28 over [1e-18, 1e18] (checked on the device)."""
+    assert gpu.selftest(0, 1 << 30, seed=1) == 0
+    assert gpu.selftest(1, 1 << 28, seed=2) == 0
