@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libptina_b200.so')
 SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu']
-HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', '../../include/ptina_b200.h']
+HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', 'ptb_trace_kernel.cuh', '../../include/ptina_b200.h']
 
 # -fmad=false / -prec-div / -prec-sqrt / -ftz=false: IEEE binary32 in source order -- what makes Morton codes, primary
 # rays and the box/triangle predicates bit-identical to a strict CPU evaluation (DESIGN.md "Arithmetic contract").

@@ -102,7 +102,7 @@ struct ptb_ctx {
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
     int counting = 0;
-    int blocks_extend = 0, blocks_shadow = 0, blocks_generic = 0;
+    int blocks_extend = 0, blocks_shadow = 0, blocks_ref = 0, blocks_generic = 0;
     std::vector<StageEvent> events;
     std::vector<cudaEvent_t> event_pool;
     int profiling = 0;

@@ -19,6 +19,7 @@
 // generator state is carried.
 #include <cstdio>
 #include "ptb_internal.h"
+#include "ptb_trace_kernel.cuh"
 
 namespace {
 
@@ -83,6 +84,7 @@ __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, 
 }
 
 __global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
+__global__ void k_ctrl_tap(Ctrl* c, int m) { c->pad[0] = m; c->pad[1] = 0; }
 __global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
 
 // ---- path.py:85-93 do_render (first half) / brute.py:66-73 -----------------------------------------------------------
@@ -114,94 +116,6 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
         block_append(live, p, queue, &ctrl->n_in, s_warp, &s_base);
     }
     if (ctr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->paths, (unsigned long long)nsamp * fm.nx * fm.ny);
-}
-
-// ---- extend: closest hit for every queued path (path.py:28-29) ------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(BLK) k_extend(TraceScene S, PathState st, const int* __restrict__ queue, Ctrl* ctrl, int policy, DevCounters* ctr) {
-    const int lane = threadIdx.x & 31;
-    const int count = ctrl->n_in;
-    TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
-    unsigned long long nrays = 0;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&ctrl->cur_extend, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        int idx = base + lane;
-        if (idx < count) {
-            int p = queue[idx];
-            float4 o4 = st.ray_o[p], d4 = st.ray_d[p];
-            V3 ro = mk3(o4.x, o4.y, o4.z);
-            V3 rd = normalized(mk3(d4.x, d4.y, d4.z));    // path.py:28  r.d = r.d.normalized()
-            int avoid = __float_as_int(d4.w);
-            HitRec h = policy == PTB_TRAVERSE_REFERENCE ? trace_reference<COUNT>(S, ro, rd, avoid, &C)
-                                                        : trace_ordered<false, COUNT>(S, ro, rd, avoid, PTB_INF, &C);
-            st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, d4.w);
-            st.hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1));
-            if (COUNT) nrays++;
-        }
-    }
-    if (COUNT) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            C.nodes += __shfl_xor_sync(0xffffffffu, C.nodes, o); C.boxes += __shfl_xor_sync(0xffffffffu, C.boxes, o);
-            C.tris += __shfl_xor_sync(0xffffffffu, C.tris, o); nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
-            C.max_stack = max(C.max_stack, __shfl_xor_sync(0xffffffffu, C.max_stack, o));
-        }
-        if (lane == 0) {
-            atomicAdd(&ctr->nodes, C.nodes); atomicAdd(&ctr->boxes, C.boxes); atomicAdd(&ctr->tris, C.tris);
-            atomicAdd(&ctr->extend_rays, nrays); atomicMax(&ctr->max_stack, C.max_stack);
-        }
-    }
-}
-
-// ---- shadow: occlusion of the queued NEE rays (path.py:49-55) -----------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(BLK) k_shadow(TraceScene S, PathState st, const int* __restrict__ queue, Ctrl* ctrl, int policy, DevCounters* ctr) {
-    const int lane = threadIdx.x & 31;
-    const int count = ctrl->n_shadow;
-    TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
-    unsigned long long nrays = 0;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&ctrl->cur_shadow, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= count) break;
-        int idx = base + lane;
-        if (idx < count) {
-            int p = queue[idx];
-            float4 o4 = st.ray_o[p], d4 = st.sh_d[p];
-            V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);   // Ray(hitpos, li.dir): NOT re-normalised
-            int avoid = __float_as_int(st.ray_d[p].w);
-            float dis = d4.w;
-            bool occluded;
-            if (policy == PTB_TRAVERSE_REFERENCE) {
-                HitRec h = trace_reference<COUNT>(S, ro, rd, avoid, &C);
-                occluded = !(h.hit == 0 || h.depth > dis);
-            } else {
-                HitRec h = trace_ordered<true, COUNT>(S, ro, rd, avoid, dis, &C);
-                occluded = h.hit != 0;
-            }
-            if (!occluded) {
-                float4 r = st.result[p], c4 = st.sh_c[p];
-                st.result[p] = make_float4(r.x + c4.x, r.y + c4.y, r.z + c4.z, r.w);
-            }
-            if (COUNT) nrays++;
-        }
-    }
-    if (COUNT) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            C.nodes += __shfl_xor_sync(0xffffffffu, C.nodes, o); C.boxes += __shfl_xor_sync(0xffffffffu, C.boxes, o);
-            C.tris += __shfl_xor_sync(0xffffffffu, C.tris, o); nrays += __shfl_xor_sync(0xffffffffu, nrays, o);
-            C.max_stack = max(C.max_stack, __shfl_xor_sync(0xffffffffu, C.max_stack, o));
-        }
-        if (lane == 0) {
-            atomicAdd(&ctr->nodes, C.nodes); atomicAdd(&ctr->boxes, C.boxes); atomicAdd(&ctr->tris, C.tris);
-            atomicAdd(&ctr->shadow_rays, nrays); atomicMax(&ctr->max_stack, C.max_stack);
-        }
-    }
 }
 
 // ---- model.py:88-101 get_geometries + geometries.py:96-108 -------------------------------------------------------------------
@@ -390,24 +304,6 @@ __global__ void __launch_bounds__(BLK) k_gather_primary(FrameMap fm, PathState s
     }
 }
 
-__global__ void __launch_bounds__(BLK) k_intersect_tap(TraceScene S, const float* __restrict__ rays, const int* __restrict__ avoid, const float* __restrict__ dis, int m,
-                                                       int policy, int anyhit, int* hit, float* depth, int* index, float* uv) {
-    int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= m) return;
-    V3 ro = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), rd = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
-    int av = avoid ? avoid[i] : -1;
-    TraceCounters C;
-    HitRec h;
-    if (anyhit) {
-        float d = dis[i];
-        if (policy == PTB_TRAVERSE_REFERENCE) { h = trace_reference<false>(S, ro, rd, av, &C); hit[i] = !(h.hit == 0 || h.depth > d); }
-        else { h = trace_ordered<true, false>(S, ro, rd, av, d, &C); hit[i] = h.hit != 0; }
-        return;
-    }
-    h = policy == PTB_TRAVERSE_REFERENCE ? trace_reference<false>(S, ro, rd, av, &C) : trace_ordered<false, false>(S, ro, rd, av, PTB_INF, &C);
-    hit[i] = h.hit; depth[i] = h.depth; index[i] = h.index; uv[2 * i] = h.u; uv[2 * i + 1] = h.v;
-}
-
 PTB_D Disney disney_from(const float* p) {
     Disney m;
     m.basecolor = mk3(p[0], p[1], p[2]); m.metallic = p[3]; m.roughness = p[4]; m.specular = p[5]; m.specularTint = p[6];
@@ -581,6 +477,22 @@ inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 }  // namespace
 
 // ================================================= host side ==========================================================
+// one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
+template <class IO>
+static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int* cursor, const int* count_ptr) {
+    DevCounters* ctr = c->counting ? c->d_counters : nullptr;
+    cudaStream_t st = c->stream;
+    if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
+        if (c->counting) k_trace_ref<IO, true><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        else k_trace_ref<IO, false><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+    } else {
+        int blocks = IO::kAnyHit ? c->blocks_shadow : c->blocks_extend;
+        if (c->counting) k_trace<IO, true><<<blocks, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        else k_trace<IO, false><<<blocks, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+    }
+    c->launches++;
+}
+
 void ptb_stage_begin(ptb_ctx* c, int stage) {
     if (!c->profiling) return;
     StageEvent ev; ev.stage = stage;
@@ -620,10 +532,12 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
     int occ = 0;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ExtendIO, false>, PTB_TRACE_BLK, 0));
     c->blocks_extend = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shadow<false>, BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ShadowIO, false>, PTB_TRACE_BLK, 0));
     c->blocks_shadow = c->sm_count * (occ > 0 ? occ : 4);
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_ref<ExtendIO, false>, PTB_TRACE_BLK, 0));
+    c->blocks_ref = c->sm_count * (occ > 0 ? occ : 4);
     c->blocks_generic = c->sm_count * 8;
     return 0;
 }
@@ -664,20 +578,17 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     int cur = 0;
     for (int depth = 1; depth <= 5; depth++) {
         ptb_stage_begin(c, ST_EXTEND);
-        if (c->counting) k_extend<true><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[cur], c->d_ctrl, policy, ctr);
-        else k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[cur], c->d_ctrl, policy, ctr);
+        { ExtendIO io; io.st = c->st; io.queue = c->d_queue[cur]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
         ptb_stage_end(c);
         ptb_stage_begin(c, ST_SHADE);
         k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, rngtab, dim, rng_stride, fm, c->st,
                                                             c->d_queue[cur], c->d_queue[cur ^ 1], c->d_shadowq, c->d_ctrl);
         ptb_stage_end(c);
-        c->launches += 2;
+        c->launches += 1;
         if (ENGINE == PTB_ENGINE_PATH) {
             ptb_stage_begin(c, ST_SHADOW);
-            if (c->counting) k_shadow<true><<<c->blocks_shadow, BLK, 0, st>>>(S, c->st, c->d_shadowq, c->d_ctrl, policy, ctr);
-            else k_shadow<false><<<c->blocks_shadow, BLK, 0, st>>>(S, c->st, c->d_shadowq, c->d_ctrl, policy, ctr);
+            { ShadowIO io; io.st = c->st; io.queue = c->d_shadowq; launch_trace(c, S, io, policy, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow); }
             ptb_stage_end(c);
-            c->launches++;
         }
         k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
         c->launches++;
@@ -732,13 +643,13 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
             TraceScene S = ptb_trace_scene(c);
             int policy = ptb_effective_policy(c, c->traversal_request);
             ptb_stage_begin(c, ST_EXTEND);
-            k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[0], c->d_ctrl, policy, nullptr);
+            { ExtendIO io; io.st = c->st; io.queue = c->d_queue[0]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
             ptb_stage_end(c);
             ptb_stage_begin(c, ST_ACCUM);
             size_t pass = (size_t)c->caps.max_filmsize;
             k_preview<<<nblk(fm.pps), BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, fm, ns, c->st, c->d_film + pass, c->d_film + 2 * pass);
             ptb_stage_end(c);
-            c->launches += 2;
+            c->launches += 1;
             continue;
         }
         int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, c->d_sobolP, c->sobol_dim, 0, fm)
@@ -768,10 +679,10 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
         if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
         TraceScene S = ptb_trace_scene(c);
         int policy = ptb_effective_policy(c, c->traversal_request);
-        k_extend<false><<<c->blocks_extend, BLK, 0, st>>>(S, c->st, c->d_queue[0], c->d_ctrl, policy, nullptr);
+        { ExtendIO io; io.st = c->st; io.queue = c->d_queue[0]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
         k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, nullptr, hit_dev, depth_dev, index_dev, uv_dev, 1);
     }
-    c->launches += 5;
+    c->launches += 4;
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -780,8 +691,11 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
                      int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev) {
     if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
     TraceScene S = ptb_trace_scene(c);
-    k_intersect_tap<<<nblk(m), BLK, 0, c->stream>>>(S, rays_dev, avoid_dev, dis_dev, m, ptb_effective_policy(c, policy), anyhit, hit_dev, depth_dev, index_dev, uv_dev);
+    k_ctrl_tap<<<1, 1, 0, c->stream>>>(c->d_ctrl, m);
     c->launches++;
+    int eff = ptb_effective_policy(c, policy);
+    if (anyhit) { TapIO<true> io{rays_dev, avoid_dev, dis_dev, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
+    else { TapIO<false> io{rays_dev, avoid_dev, dis_dev, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
