@@ -124,6 +124,9 @@ int ptb_render_range(ptb_ctx* ctx, int engine, int k_first, int count, int strid
 /* mltpath.py:30-36 reset(); LSP / Sigma fields mltpath.py:23-33 */
 int ptb_mlt_reset(ptb_ctx* ctx, uint64_t seed, int chain_first, int chain_count);
 int ptb_mlt_set_param(ptb_ctx* ctx, float lsp, float sigma);
+/* tap: the chains' last proposal X_new [count][32] and its radiance L_new [count][3] (mltpath.py:56-75), and the current
+ * state X_old / L_old; any pointer may be NULL */
+int ptb_mlt_state(ptb_ctx* ctx, float* x_new, float* l_new, float* x_old, float* l_old);
 
 /* filmtable.py:47-63 get_image: out [nx][ny][4];  filmtable.py:65-79 fast_export_image: out [ny*nx*3] */
 int ptb_get_image(ptb_ctx* ctx, int pass, float* out, int memspace);

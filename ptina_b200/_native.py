@@ -46,7 +46,7 @@ SYMBOLS = [
     'ptb_set_sobol_table', 'ptb_sobol_reset', 'ptb_sobol_get_time', 'ptb_sobol_set_time', 'ptb_sobol_point',
     'ptb_load_model', 'ptb_load_materials', 'ptb_load_images', 'ptb_clear_lights', 'ptb_add_light', 'ptb_set_world_light',
     'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
-    'ptb_film_ptr', 'ptb_render', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_get_image',
+    'ptb_film_ptr', 'ptb_render', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_mlt_state', 'ptb_get_image',
     'ptb_fast_export_image', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
     'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_render_sample',
     'ptb_set_counting', 'ptb_get_counters', 'ptb_reset_counters', 'ptb_get_stage_ms', 'ptb_get_launches', 'ptb_measure_l2', 'ptb_selftest',
@@ -289,6 +289,12 @@ class Context:
 
     def mlt_reset(self, seed=0, chain_first=0, chain_count=2**18):
         self._check(self.L.ptb_mlt_reset(self.h, ctypes.c_uint64(seed), int(chain_first), int(chain_count)))
+
+    def mlt_state(self, nchains):
+        xn, xo = np.empty((nchains, 32), np.float32), np.empty((nchains, 32), np.float32)
+        ln, lo = np.empty((nchains, 3), np.float32), np.empty((nchains, 3), np.float32)
+        self._check(self.L.ptb_mlt_state(self.h, _ptr(xn), _ptr(ln), _ptr(xo), _ptr(lo)))
+        return dict(X_new=xn, L_new=ln, X_old=xo, L_old=lo)
 
     def mlt_set_param(self, lsp, sigma):
         self._check(self.L.ptb_mlt_set_param(self.h, ctypes.c_float(lsp), ctypes.c_float(sigma)))

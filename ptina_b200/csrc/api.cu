@@ -332,6 +332,24 @@ int ptb_mlt_reset(ptb_ctx* c, uint64_t seed, int chain_first, int chain_count) {
     c->mlt_seed = seed; c->mlt_first = chain_first; c->mlt_count = chain_count;
     return ptb_wf_mlt_reset(c);
 }
+int ptb_mlt_state(ptb_ctx* c, float* x_new, float* l_new, float* x_old, float* l_old) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    int n = c->mlt_count;
+    if (n <= 0) { ptb_set_error("MLT chains not initialised (ptb_mlt_reset)"); return 1; }
+    cudaStream_t s = c->stream;
+    std::vector<float> tmp((size_t)n * 4);
+    if (x_new) PTB_CUDA(cudaMemcpyAsync(x_new, c->d_Xnew, sizeof(float) * 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (x_old) PTB_CUDA(cudaMemcpyAsync(x_old, c->d_Xold, sizeof(float) * 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    PTB_CUDA(cudaStreamSynchronize(s));
+    for (int which = 0; which < 2; which++) {
+        float* dst = which == 0 ? l_new : l_old;
+        if (!dst) continue;
+        PTB_CUDA(cudaMemcpy(tmp.data(), which == 0 ? (const void*)c->st.result : (const void*)c->d_Lold, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) { dst[3 * i] = tmp[4 * i]; dst[3 * i + 1] = tmp[4 * i + 1]; dst[3 * i + 2] = tmp[4 * i + 2]; }
+    }
+    return 0;
+}
 int ptb_mlt_set_param(ptb_ctx* c, float lsp, float sigma) { CHECK_CTX(c); c->mlt_lsp = lsp; c->mlt_sigma = sigma; return 0; }
 
 static int resolve_common(ptb_ctx* c, int pass, int mode, float* out, int memspace, size_t count) {

@@ -384,3 +384,55 @@ def test_exact_division_shortcut(gpu):
     bit on 2^30 operand pairs in the slab test's ranges and 2^28 over [1e-18, 1e18] (checked on the device)."""
     assert gpu.selftest(0, 1 << 30, seed=1) == 0
     assert gpu.selftest(1, 1 << 28, seed=2) == 0
+
+
+def test_mlt_engine(gpu):
+    """Config 5 (engine/mltpath.py): per-chain parity of the proposal's radiance against the oracle's path_trace driven by the same
+    32-D sample vector (RNGProxy), the accept/reject bookkeeping, and statistical agreement of the MLT image with the path tracer.
+    ti.random() cannot be reproduced (Philox here), so the chain trajectories themselves are 'parity unpinned'."""
+    from ptina_b200.engine import MLTPathEngine
+    sc, o = load(gpu, 'cornell_monkey', (64, 64))
+    nch = 1 << 14
+    eng = MLTPathEngine(nchains=nch, seed=7)
+    eng.LSP[None] = 0.25; eng.Sigma[None] = 0.01
+    eng.reset()
+    worker.clear()
+    eng.render(1)
+    st = gpu.mlt_state(nch)
+    X = st['X_new']
+    assert X.min() >= 0.0 and X.max() < 1.0
+    ref = o.trace_from_samples(X)
+    rel = np.abs(st['L_new'] - ref).max(1) / np.maximum(np.abs(ref).max(1), 1e-2)
+    assert np.median(rel) < 1e-6 and (rel > 1e-4).mean() < 5e-3, (float(np.median(rel)), float((rel > 1e-4).mean()))
+    # first iteration: L_old = 0 -> accept = min(1, (avg(L_new)+1e-10)/1e-10) = 1 for every chain (mltpath.py:76-81)
+    assert np.array_equal(st['X_old'], X) and np.array_equal(st['L_old'], st['L_new'])
+    film = gpu.get_film()
+    assert film[..., 3].sum() == nch                       # one splat of weight 1 per chain (mltpath.py:47-52)
+    # large steps ~ LSP of the chains on the second iteration; small steps move by ~Sigma
+    eng.render(1)
+    st2 = gpu.mlt_state(nch)
+    moved = np.abs(st2['X_new'] - st['X_old'])
+    moved = np.minimum(moved, 1 - moved)                    # distance on the unit torus
+    small = moved.max(1) < 0.1
+    assert 0.70 < small.mean() < 0.80, small.mean()
+    assert 0.006 < moved[small].std() < 0.014
+    # accept/reject (mltpath.py:76-81): accept = min(1, (avg L_new + 1e-10) / (avg L_old + 1e-10)); accepted <=> X_old := X_new
+    a_new, a_old = st2['L_new'].mean(1) + 1e-10, st['L_old'].mean(1) + 1e-10
+    accept = np.minimum(1.0, a_new / a_old)
+    accepted = (st2['X_old'] == st2['X_new']).all(1)
+    assert accepted[accept >= 1.0].all()                                   # never rejects an uphill move
+    assert not accepted[a_new <= 1e-9].any() or (a_old <= 1e-9).any()       # a black proposal is (almost) never accepted
+    mid = (accept > 0.05) & (accept < 0.95)
+    assert mid.sum() > 500 and abs(accepted[mid].mean() - accept[mid].mean()) < 0.05
+    assert np.array_equal(st2['L_old'][accepted], st2['L_new'][accepted]) and np.array_equal(st2['L_old'][~accepted], st['L_old'][~accepted])
+    # MLT image vs path-traced image: the reference splats every PROPOSAL with weight 1 (mltpath.py:47-52, 73-74), so its image is
+    # the per-pixel mean of proposed radiance -- brighter than the path tracer's mean, not an unbiased estimate; same order of magnitude
+    for _ in range(40):
+        eng.render(1)
+    mlt = worker.get_image()[..., :3]
+    worker.clear(); gpu.sobol_reset()
+    gpu.render(_native.ENGINE_PATH, 64)
+    pt = worker.get_image()[..., :3]
+    valid = gpu.get_film()[..., 3] > 0
+    ratio = mlt[valid].mean() / pt[valid].mean()
+    assert 0.8 < ratio < 2.5, ratio
