@@ -181,6 +181,7 @@ def run_gpu(args):
     ev1.record()
     barrier()
     sampler.stop_flag = True
+    sampler.join(timeout=10)      # an nvidia-smi query still in flight perturbs the host-synchronous e2e loop below
     ms = ev0.elapsed_time(ev1)
     stage = ctx.stage_ms(); launches = ctx.launches()
     ctx.set_counting(False, False)
@@ -202,24 +203,35 @@ def run_gpu(args):
     from ptina_b200.model import ModelPool
     from ptina_b200.tree import BVHTree
 
+    e2e_parts = {}
+
     def e2e_step():
-        ModelPool().load(verts_pin.numpy(), mtl_pin.numpy())
-        BVHTree().build()
+        t = [time.perf_counter()]
+        ModelPool().load(verts_pin.numpy(), mtl_pin.numpy()); t.append(time.perf_counter())
+        BVHTree().build(); t.append(time.perf_counter())
         worker.clear()
-        frame()
+        frame(); t.append(time.perf_counter())
         if rank == 0:
             ctx.get_image(0, out=img_pin.numpy())
         else:
             ctx.synchronize()
+        t.append(time.perf_counter())
+        for name, a, b in zip(('load', 'build', 'launch', 'wait+readback'), t[:-1], t[1:]):
+            e2e_parts.setdefault(name, []).append(round((b - a) * 1e3, 2))
     for _ in range(max(1, args.warmup)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    dbg = []
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         e2e_step()
+        dbg.append((time.perf_counter() - t1) * 1e3)
     e1.record()
+    if os.environ.get('PTB_BENCH_DEBUG'):
+        print('e2e per-step wall ms:', [round(x, 2) for x in dbg], {k: v[-args.steps:] for k, v in e2e_parts.items()}, file=sys.stderr)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     t = torch.tensor([e2e_ms], device='cuda')

@@ -194,9 +194,13 @@ __global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P
                         float mis = power_heuristic(li.pdf, brdf_pdf);
                         V3 direct = mis * li.color * brdf_clr * dot_or_zero(normal, li.dir);
                         V3 contrib = thr * direct;
-                        st.sh_d[p] = make_float4(li.dir.x, li.dir.y, li.dir.z, li.dis);
-                        st.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
-                        want_shadow = true;
+                        // a contribution that is exactly zero (light sample below the horizon, black throughput) adds nothing whether or
+                        // not the shadow ray is blocked, so the ray is not traced; NaNs compare unequal and still go through
+                        if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
+                            st.sh_d[p] = make_float4(li.dir.x, li.dir.y, li.dir.z, li.dis);
+                            st.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+                            want_shadow = true;
+                        }
                     }
                     c0 += 3;
                 } else {
