@@ -107,3 +107,15 @@ def test_multimesh_contract():
     v, m = compose_multiple_meshes([(p, n, None, mx.translate((1, 2, 3)) @ mx.scale(2), 5), (p, n, None, np.eye(4), None)])
     assert v.shape == (6, 8) and m.tolist() == [5, -1]
     assert np.allclose(v[1, :3], [3, 2, 3]) and np.allclose(v[0, 3:6], [0, 0, 1]) and np.allclose(v[:, 6:], 0)
+
+
+def test_readobj_roundtrip(tmp_path):
+    import numpy as np
+    from ptina_b200.tools.readobj import readobj
+    p = tmp_path / 'quad.obj'
+    p.write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1 4/4/1\n')
+    o = readobj(str(p))
+    assert o['f'].shape == (2, 3, 3) and o['v'].shape == (4, 3)
+    assert o['f'][1, :, 0].tolist() == [0, 2, 3] and o['f'][0, :, 1].tolist() == [0, 1, 2]
+    verts = o['v'][o['f'][:, :, 0]].reshape(-1, 3)
+    assert np.allclose(verts[3], [0, 0, 0]) and np.allclose(verts[5], [0, 1, 0])
