@@ -35,7 +35,8 @@ enum { PTB_ENGINE_PATH = 0, PTB_ENGINE_BRUTE = 1, PTB_ENGINE_PREVIEW = 2, PTB_EN
 enum { PTB_LIGHT_POINT = 1, PTB_LIGHT_AREA = 2 };            /* light/__init__.py:11 */
 enum { PTB_TRAVERSE_AUTO = 0,      /* ordered + culled when the tree validates, else reference order */
        PTB_TRAVERSE_REFERENCE = 1, /* lbvh.py:313-347 literally: unordered child1-first DFS, no culling */
-       PTB_TRAVERSE_ORDERED = 2 };
+       PTB_TRAVERSE_ORDERED = 2,   /* near-first, distance-culled; conservative box tests + exact gate test on acceptance */
+       PTB_TRAVERSE_ORDERED_EXACT = 3 /* the same order with the exact (division-equivalent) slab test at every node */ };
 
 /* things.py:12-19 init_things(...) capacities.  Zero fields take the reference defaults. */
 typedef struct ptb_caps {

@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, 'libptina_b200.so')
 HOST, DEVICE = 0, 1
 ENGINE_PATH, ENGINE_BRUTE, ENGINE_PREVIEW, ENGINE_MLT = 0, 1, 2, 3
 LIGHT_TYPES = {'POINT': 1, 'AREA': 2}            # light/__init__.py:11
-TRAVERSE_AUTO, TRAVERSE_REFERENCE, TRAVERSE_ORDERED = 0, 1, 2
+TRAVERSE_AUTO, TRAVERSE_REFERENCE, TRAVERSE_ORDERED, TRAVERSE_ORDERED_EXACT = 0, 1, 2, 3
 
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_i32p = ctypes.POINTER(ctypes.c_int32)

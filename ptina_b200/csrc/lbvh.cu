@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
 
 // packed 64-byte node: both children's boxes (leaf child: the triangle's bounds)
 __global__ void __launch_bounds__(BLK) k_pack_nodes(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child,
-                                                    const float* __restrict__ bmin, const float* __restrict__ bmax, int n, Node64* nodes) {
+                                                    const float* __restrict__ bmin, const float* __restrict__ bmax, int n, Node64* nodes, int* __restrict__ gate) {
     int i = blockIdx.x * BLK + threadIdx.x;
     if (i >= n - 1) return;
     int2 ch = child[i];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const float* __restrict__ ve
     for (int k = 0; k < 2; k++) {
         int c = k == 0 ? ch.x : ch.y;
         if (c < 0 || c >= 2 * n - 1) { lo[k] = v3s(0.0f); hi[k] = v3s(0.0f); }
-        else if (c < n) face_box(verts, leaf[c], &lo[k], &hi[k]);
+        else if (c < n) { face_box(verts, leaf[c], &lo[k], &hi[k]); gate[c] = i; }
         else { int j = c - n; lo[k] = mk3(bmin[3 * j], bmin[3 * j + 1], bmin[3 * j + 2]); hi[k] = mk3(bmax[3 * j], bmax[3 * j + 1], bmax[3 * j + 2]); }
     }
     Node64 N;
@@ -307,7 +307,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
             return 2;
         }
         k_validate<<<nblk(2 * n - 1), BLK, 0, st>>>(c->d_parentcnt, n, c->d_scalars);
-        k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, c->d_bmin, c->d_bmax, n, c->d_nodes);
+        k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, c->d_bmin, c->d_bmax, n, c->d_nodes, c->d_gate);
         c->launches += 2;
     }
     if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }

@@ -20,16 +20,18 @@ void ptb_set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-// SoA wavefront state, one entry per path in flight (HBM; 7 x 16 B per path)
+// SoA wavefront state, one entry per path in flight (HBM; 5 x 16 B per path)
 struct PathState {
-    float4* ray_o;    // origin xyz, w = last_brdf_pdf            (path.py:22,61)
-    float4* ray_d;    // direction xyz, w = avoid id (int bits)   (path.py:19,40)
-    float4* hit;      // depth, u, v, face id (int bits; -1 = miss)
+    float4* ray_o;    // camera ray origin (written by raygen; read by the taps and the preview pass)
+    float4* ray_d;    // camera ray direction as Camera.generate returns it
+    float4* hit;      // depth, u, v, face id (int bits; -1 = miss)                        -- written by extend
     float4* thr;      // throughput rgb (path.py:21), w = depth counter (int bits)
-    float4* result;   // radiance rgb (path.py:20)
-    float4* sh_d;     // shadow ray direction xyz, w = distance to the light sample
-    float4* sh_c;     // contribution to add if the shadow ray is unoccluded
+    float4* result;   // radiance rgb (path.py:20), w = last_brdf_pdf (path.py:22,61)
 };
+// Ray queues hold self-contained records in queue order (coalesced for the consumer, stageable with cp.async):
+//   extend : o = (origin, path slot)  d = (unit direction, avoid leaf slot)               -- written by raygen / shade
+//   shadow : o = (origin, path slot)  d = (direction, distance to the light sample)  c = (contribution if unoccluded, avoid leaf slot)
+struct RayQueue { float4* o; float4* d; float4* c; };
 
 // device-side control block: queue sizes and work cursors
 struct Ctrl {
@@ -38,6 +40,8 @@ struct Ctrl {
     int n_shadow;    // entries in the shadow queue
     int cur_extend, cur_shadow;
     int pad[3];
+    int special[2];  // rays set aside for the exact-test kernel: count, cursor
+    int pad2[2];
 };
 
 struct DevCounters {
@@ -84,6 +88,7 @@ struct ptb_ctx {
     Node64* d_nodes = nullptr;
     Tri64* d_tris = nullptr;
     int32_t* d_slot_of = nullptr;   // face id -> leaf slot
+    int32_t* d_gate = nullptr;      // leaf slot -> parent internal node (the box that gates its triangle test)
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)
     ptb_tree_info tree_info{};
@@ -97,12 +102,15 @@ struct ptb_ctx {
     // ---- wavefront ----
     int64_t max_paths = 0;
     PathState st{};
-    int* d_queue[2] = {nullptr, nullptr};
-    int* d_shadowq = nullptr;
+    RayQueue xq[2]{};               // extend queues (in / out, swapped every bounce)
+    RayQueue sq{};                  // shadow queue
+    int* d_specialq = nullptr;      // queue positions of rays the conservative kernel set aside
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
     int counting = 0;
-    int blocks_extend = 0, blocks_shadow = 0, blocks_ref = 0, blocks_generic = 0;
+    int smem_optin = 0;             // opt-in shared memory per block (227 KB on B200)
+    bool no_resident_bvh = false;   // PTB_NO_RESIDENT_BVH=1: never use the shared-memory-resident traversal variant
+    int blocks_extend = 0, blocks_shadow = 0, blocks_ref = 0, blocks_generic = 0, blocks_exact = 0;
     std::vector<StageEvent> events;
     std::vector<cudaEvent_t> event_pool;
     int profiling = 0;

@@ -1,73 +1,108 @@
 // ptb_trace_kernel.cuh -- the traversal kernels.
 //
-//  k_trace      : production kernel.  Persistent warps; every lane owns one ray and keeps its traversal state in
-//                 registers (+ a local-memory stack).  A lane that finishes its ray takes the next one from a warp-local
-//                 pool of queue indices (refilled 256 at a time with one atomic), so lanes do not idle while the
-//                 slowest ray of a 32-ray batch finishes.  Every iteration the warp votes for ONE kind of step -- a node
-//                 step (fetch a 64-B node, two exact slab tests, push/descend) or a leaf step (one triangle test from the
-//                 lane's small queue of pending leaves) -- whichever more lanes can take, so that the lanes of a warp run
-//                 the same code.  Deferring a triangle test never changes the result: acceptance is `depth < best`, ties
-//                 go to the larger leaf slot.  Same predicates as trace_ordered in ptb_traverse.cuh; results are
-//                 bit-identical to trace_reference.
-//  k_trace_ref  : the reference's literal traversal (lbvh.py:313-347), one ray per thread; used when the tree is not
-//                 a proper tree, when PTB_TRAVERSE_REFERENCE is requested, and by the tests as the on-device checker.
-//
-// Ray sources/sinks (IO): the wavefront's extend and shadow queues, and flat arrays for the parity taps.
+//  k_trace       : production kernel.  Persistent warps; every lane owns one ray and keeps its traversal state in registers
+//                  (stack: top entry in a register, the rest in local memory).  Rays arrive as self-contained RECORDS in
+//                  queue order (origin|path, direction|avoid slot, [contribution|tmax]); a warp stages them 32 at a time into a
+//                  double-buffered shared-memory tile with cp.async, so the DRAM latency of the next tile is covered by the
+//                  traversal of the current one.  A lane that finishes its ray takes the next staged record.  Every iteration
+//                  the warp votes for ONE kind of step -- a node step (fetch a 64-B node, two conservative slab tests, push /
+//                  descend) or a leaf step (one triangle test from the lane's ring of pending leaves in shared memory) --
+//                  whichever more lanes can take.  Box tests are conservative (1 FMA per plane); the exact reference test is
+//                  evaluated on the gate box of a triangle that is about to be accepted (ptb_traverse.cuh).  Results are
+//                  bit-identical to trace_reference.
+//  k_trace_simple: one ray per thread.  POLICY 0 = the reference's literal traversal (lbvh.py:313-347): used when the tree is not a
+//                  proper tree, when PTB_TRAVERSE_REFERENCE is requested, and by the tests as the on-device checker.
+//                  POLICY 1 = trace_ordered (exact slab test at every node): traces the rays k_trace sets aside (axis-parallel /
+//                  non-finite) and is the PTB_TRAVERSE_ORDERED_EXACT checker.
 #pragma once
 #include "ptb_internal.h"
 
 #define PTB_TRACE_BLK 128
-#define PTB_TRACE_CHUNK 256
-#ifndef PTB_NODE_STEPS
-#define PTB_NODE_STEPS 3
+#define PTB_TILE 32                 /* ray records per staged tile (one per lane) */
+#ifndef PTB_FETCH_MIN
+#define PTB_FETCH_MIN 6             /* idle lanes that trigger a refill from the staged tile */
 #endif
 
-// ---- extend queue: closest hit for path p (path.py:28-29) ----------------------------------------------------------------
+struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; };
+
+// ---- extend queue: closest hit for path p (path.py:28-29).  Records: q0 = (origin, path), q1 = (unit direction, avoid slot) -------
 struct ExtendIO {
-    PathState st; const int* __restrict__ queue;
     static constexpr bool kAnyHit = false;
-    PTB_D void load(int idx, int* item, V3* ro, V3* rd, int* avoid, float* tmax) const {
-        int p = queue[idx];
-        float4 o4 = st.ray_o[p], d4 = st.ray_d[p];
-        *item = p; *ro = mk3(o4.x, o4.y, o4.z);
-        *rd = normalized(mk3(d4.x, d4.y, d4.z));                  // path.py:28  r.d = r.d.normalized()
-        st.ray_d[p] = make_float4(rd->x, rd->y, rd->z, d4.w);
-        *avoid = __float_as_int(d4.w); *tmax = PTB_INF;
+    static constexpr int K = 2;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; float4* hit;
+    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : q1; }
+    PTB_D void decode(const float4* r, RayIn* in) const {
+        in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->avoid_slot = __float_as_int(r[1].w); in->tmax = PTB_INF;
     }
-    PTB_D void store(int p, const HitRec& h) const { st.hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1)); }
+    PTB_D void store(int p, const HitRec& h, V3) const { hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1)); }
 };
-// ---- shadow queue: Ray(hitpos, li.dir) against avoid = hit triangle; unoccluded -> add the pending contribution (path.py:49-55)
+// ---- shadow queue: Ray(hitpos, li.dir) against avoid = hit triangle; unoccluded -> add the pending contribution (path.py:49-55).
+// Records: q0 = (origin, path), q1 = (direction as sampled -- not re-normalised, like the reference --, distance), q2 = (contribution,
+// avoid slot).  Exactly one shadow ray per path per launch touches result[p], so the reduction `red.add` computes the same single
+// rounded sum as a load-add-store, without making the warp wait for the load.
 struct ShadowIO {
-    PathState st; const int* __restrict__ queue;
     static constexpr bool kAnyHit = true;
-    PTB_D void load(int idx, int* item, V3* ro, V3* rd, int* avoid, float* tmax) const {
-        int p = queue[idx];
-        float4 o4 = st.ray_o[p], d4 = st.sh_d[p];
-        *item = p; *ro = mk3(o4.x, o4.y, o4.z); *rd = mk3(d4.x, d4.y, d4.z);   // not re-normalised, as in the reference
-        *avoid = __float_as_int(st.ray_d[p].w); *tmax = d4.w;
+    static constexpr int K = 3;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2; float4* result;
+    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
+    PTB_D void decode(const float4* r, RayIn* in) const {
+        in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->tmax = r[1].w;
+        in->c = mk3(r[2].x, r[2].y, r[2].z); in->avoid_slot = __float_as_int(r[2].w);
     }
-    PTB_D void store(int p, const HitRec& h) const {
+    PTB_D void store(int p, const HitRec& h, V3 c) const {
         if (h.hit) return;
-        float4 r = st.result[p], c4 = st.sh_c[p];
-        st.result[p] = make_float4(r.x + c4.x, r.y + c4.y, r.z + c4.z, r.w);
+        float* r = reinterpret_cast<float*>(&result[p]);
+        atomicAdd(r, c.x); atomicAdd(r + 1, c.y); atomicAdd(r + 2, c.z);
     }
 };
-// ---- parity taps: flat ray arrays ----------------------------------------------------------------------------------------------
+// ---- parity taps: the same record formats (written by k_pack_tap), results into flat arrays -------------------------------------------
 template <bool ANYHIT>
 struct TapIO {
-    const float* __restrict__ rays; const int* __restrict__ avoid; const float* __restrict__ dis;
-    int* hit; float* depth; int* index; float* uv;
     static constexpr bool kAnyHit = ANYHIT;
-    PTB_D void load(int idx, int* item, V3* ro, V3* rd, int* av, float* tmax) const {
-        *item = idx;
-        *ro = mk3(rays[6 * idx], rays[6 * idx + 1], rays[6 * idx + 2]); *rd = mk3(rays[6 * idx + 3], rays[6 * idx + 4], rays[6 * idx + 5]);
-        *av = avoid ? avoid[idx] : -1; *tmax = ANYHIT ? dis[idx] : PTB_INF;
+    static constexpr int K = ANYHIT ? 3 : 2;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2;
+    int* hit; float* depth; int* index; float* uv;
+    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
+    PTB_D void decode(const float4* r, RayIn* in) const {
+        in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
+        in->rd = mk3(r[1].x, r[1].y, r[1].z);
+        if (ANYHIT) { in->tmax = r[1].w; in->avoid_slot = __float_as_int(r[2].w); }
+        else { in->tmax = PTB_INF; in->avoid_slot = __float_as_int(r[1].w); }
     }
-    PTB_D void store(int i, const HitRec& h) const {
+    PTB_D void store(int i, const HitRec& h, V3) const {
         hit[i] = h.hit;
         if (!ANYHIT) { depth[i] = h.depth; index[i] = h.index; uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
     }
 };
+// ---- rays the production kernel set aside (axis-parallel / non-finite): queue positions listed in `list` -----------------------
+template <class IO>
+struct ListedIO {
+    static constexpr bool kAnyHit = IO::kAnyHit;
+    static constexpr int K = IO::K;
+    IO io; const int* __restrict__ list;
+};
+template <class IO> struct IOTraits {
+    PTB_D static int position(const IO&, int i) { return i; }
+    PTB_D static const IO& base(const IO& io) { return io; }
+};
+template <class IO> struct IOTraits<ListedIO<IO>> {
+    PTB_D static int position(const ListedIO<IO>& l, int i) { return l.list[i]; }
+    PTB_D static const IO& base(const ListedIO<IO>& l) { return l.io; }
+};
+
+// record `i` of the queue straight from global memory (one-ray-per-thread kernels)
+template <class IO>
+PTB_D void fetch_direct(const IO& io_any, int i, RayIn* in) {
+    const auto& io = IOTraits<IO>::base(io_any);
+    const int pos = IOTraits<IO>::position(io_any, i);
+    float4 r[IO::K];
+#pragma unroll
+    for (int k = 0; k < IO::K; k++) r[k] = io.rec(k)[pos];
+    in->c = v3s(0.0f);
+    io.decode(r, in);
+}
 
 template <bool COUNT>
 PTB_D void flush_counters(const TraceCounters& C, unsigned long long nrays, bool shadow, DevCounters* ctr) {
@@ -84,9 +119,9 @@ PTB_D void flush_counters(const TraceCounters& C, unsigned long long nrays, bool
     }
 }
 
-// reference policy: one ray per thread, static chunks of 32 per warp
-template <class IO, bool COUNT>
-__global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_ref(TraceScene S, IO io, int* cursor, const int* count_ptr, DevCounters* ctr) {
+// one ray per thread, chunks of 32 per warp.  POLICY 0: the reference's literal order; 1: trace_ordered (exact slab tests)
+template <class IO, int POLICY, bool COUNT>
+__global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO io, int* cursor, const int* count_ptr, DevCounters* ctr) {
     const int lane = threadIdx.x & 31;
     const int count = *count_ptr;
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
@@ -98,160 +133,228 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_ref(TraceScene S, IO io
         if (base >= count) break;
         int idx = base + lane;
         if (idx < count) {
-            int item, avoid; V3 ro, rd; float tmax;
-            io.load(idx, &item, &ro, &rd, &avoid, &tmax);
-            HitRec h = trace_reference<COUNT>(S, ro, rd, avoid, &C);
-            if (IO::kAnyHit) h.hit = !(h.hit == 0 || h.depth > tmax);       // path.py:50  occ.hit == 0 or occ.depth > li.dis
-            io.store(item, h);
+            RayIn in;
+            fetch_direct(io, idx, &in);
+            const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
+            HitRec h;
+            if (POLICY == 0) {
+                h = trace_reference<COUNT>(S, in.ro, in.rd, avoid, &C);
+                if (IO::kAnyHit) h.hit = !(h.hit == 0 || h.depth > in.tmax);       // path.py:50  occ.hit == 0 or occ.depth > li.dis
+            } else {
+                h = trace_ordered<IO::kAnyHit, COUNT>(S, in.ro, in.rd, avoid, in.tmax, &C);
+            }
+            IOTraits<IO>::base(io).store(in.item, h, in.c);
             if (COUNT) nrays++;
         }
     }
     flush_counters<COUNT>(C, nrays, IO::kAnyHit, ctr);
 }
 
-// Pending-leaf queue of a lane: a ring of PTB_PQ (slot, entry distance) pairs in shared memory (column = thread, so the
-// dynamic index costs no divergence and no bank conflict).
-#define PTB_PQ 4
-struct LeafQueue {
-    int* slots; float* nears; int head, count;
-    PTB_D void clear() { head = 0; count = 0; }
-    PTB_D void push(int s, float nr) {
-        const int k = ((head + count) & (PTB_PQ - 1)) * PTB_TRACE_BLK;
-        slots[k] = s; nears[k] = nr;
-        count++;
-    }
-    PTB_D void pop(int* s, float* nr) {
-        const int k = head * PTB_TRACE_BLK;
-        *s = slots[k]; *nr = nears[k];
-        head = (head + 1) & (PTB_PQ - 1);
-        count--;
-    }
+// ---- cp.async helpers (16-byte global -> shared copies, per-thread groups) --------------------------------------------------------------
+PTB_D void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+PTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+#define PTB_PQ 4                    /* pending-leaf ring entries per lane */
+#define PTB_TRACE_BLK_S 768         /* threads of the shared-memory-resident variant (one CTA per SM) */
+
+// dynamic shared memory layout of k_trace (bytes), shared by the kernel and the host launch code
+template <int K, int BLK>
+struct TraceSmem {
+    static constexpr size_t tile = (size_t)(BLK / 32) * 2 * K * PTB_TILE * sizeof(float4);
+    static constexpr size_t queue = (size_t)PTB_PQ * BLK * (sizeof(int) + sizeof(float));
+    static constexpr size_t fixed = tile + queue;
+    __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64) + (size_t)n * sizeof(Tri64); }
 };
 
-template <class IO, bool COUNT>
-__global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace(TraceScene S, IO io, int* cursor, const int* count_ptr, DevCounters* ctr) {
+// ---- production kernel -------------------------------------------------------------------------------------------------------------------
+// SMEM = true: the whole packed BVH (nodes + triangles, 128 B per triangle) is copied into shared memory by each CTA (one CTA of
+// PTB_TRACE_BLK_S threads per SM) as four 16-byte "quarter" arrays per record type, so that a divergent 64-byte fetch costs ~4 x 7
+// shared-memory wavefronts instead of 4 x 32 L1 wavefronts (one per lane and 16-byte load) -- for incoherent rays the L1 wavefront
+// rate, not the issue rate, is what binds the global-memory variant.  Used when the BVH fits (ptb_wf: n <= ~1400 triangles).
+template <class IO, bool COUNT, int BLK, bool SMEM>
+__global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io, int* cursor, const int* count_ptr, int* __restrict__ special_list, int* special_count,
+                                                             DevCounters* ctr) {
     constexpr bool ANYHIT = IO::kAnyHit;
+    constexpr int K = IO::K;
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    constexpr int WARPS = BLK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int count = *count_ptr;
     const int n = S.n;
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
     unsigned long long nrays = 0;
 
-    int pool_next = 0, pool_end = 0;      // warp-uniform pool of queue indices
-    bool exhausted = false;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    // staged ray records: [warp][buffer][k][lane]
+    float4 (*s_tile)[2][K][PTB_TILE] = reinterpret_cast<float4 (*)[2][K][PTB_TILE]>(s_raw);
+    // pending leaves: ring of PTB_PQ (slot, lower bound of the entry distance) per lane, column = thread (no bank conflicts)
+    int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + TraceSmem<K, BLK>::tile);
+    float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + TraceSmem<K, BLK>::tile + (size_t)PTB_PQ * BLK * sizeof(int));
+    // resident BVH: quarter q of node i at s_node[q * (n-1) + i], quarter q of triangle s at s_tri[q * n + s]
+    float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<K, BLK>::fixed);
+    float4* s_tri = s_node + 4 * (size_t)(n - 1);
+    if (SMEM) {
+        const float4* gn = reinterpret_cast<const float4*>(S.nodes);
+        const float4* gt = reinterpret_cast<const float4*>(S.tris);
+        for (int i = threadIdx.x; i < 4 * (n - 1); i += BLK) s_node[(i & 3) * (n - 1) + (i >> 2)] = gn[i];
+        for (int i = threadIdx.x; i < 4 * n; i += BLK) s_tri[(i & 3) * n + (i >> 2)] = gt[i];
+        __syncthreads();
+    }
+
+    // ---- warp-uniform staging state ----
+    int tile_base0 = 0, tile_base1 = 0, tile_n0 = 0, tile_n1 = 0;   // queue position of record 0 / number of valid records, per buffer
+    int cur_buf = 0, tile_pos = 0;                                   // consumption cursor in the current buffer
+    bool tile_ready = false, exhausted = false;
+    auto fill = [&](int b) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, PTB_TILE);
+        base = __shfl_sync(FULL, base, 0);
+        const int nv = max(0, min(PTB_TILE, count - base));
+        if (lane < nv) {
+#pragma unroll
+            for (int k = 0; k < K; k++) cp_async16(&s_tile[warp][b][k][lane], io.rec(k) + base + lane);
+        }
+        cp_async_commit();
+        if (b == 0) { tile_base0 = base; tile_n0 = nv; } else { tile_base1 = base; tile_n1 = nv; }
+    };
+    fill(0); fill(1);
+
     // ---- per-lane ray state ----
-    bool have = false;
-    int item = -1, avoid_slot = -1;
-    RayPre P; P.o = v3s(0.0f); P.d = v3s(0.0f); P.r = v3s(0.0f); P.par = false;
+    int item = -1, avoid_slot = -1;            // item >= 0: this lane owns a ray (its result is stored when the lane next goes idle)
+    RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
+    V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-    int stack_id[PTB_STACK]; float stack_near[PTB_STACK];
-    int sp = 0, cur = -1;
+    // stack entries: low word = internal node | SURE_BIT (its own box certainly passes the reference's test), high word = lower
+    // bound of its entry distance.  The top lives in `tos` (valid iff sp > 0; reloaded at pop time, consumed at the next pop), the
+    // entries below it in stack[1 .. sp-1].
+    constexpr unsigned SURE_BIT = 0x80000000u;
+    unsigned long long stack[PTB_STACK + 1];
+    unsigned long long tos = 0;
+    int sp = 0;
+    int cur = -1;                              // node to visit next (| SURE_BIT), -1: take it from the stack
     float cur_near = 0.0f;
-    __shared__ int q_slots[PTB_PQ * PTB_TRACE_BLK];
-    __shared__ float q_nears[PTB_PQ * PTB_TRACE_BLK];
-    LeafQueue Q; Q.slots = q_slots + threadIdx.x; Q.nears = q_nears + threadIdx.x; Q.clear();
+    int q_head = 0, q_count = 0;
 
     while (true) {
-        // ---- fetch: idle lanes take the next queue entries (batched: at least 4 idle lanes, or nothing else to do) -------------
-        const unsigned idle = __ballot_sync(FULL, !have);
-        if (idle != 0u && !exhausted && (__popc(idle) >= 4 || idle == FULL)) {
-            if (pool_next >= pool_end) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(cursor, PTB_TRACE_CHUNK);
-                b = __shfl_sync(FULL, b, 0);
-                pool_next = b; pool_end = min(b + PTB_TRACE_CHUNK, count);
-                if (b >= count) { exhausted = true; pool_end = pool_next; }
-            }
-            const int idx = pool_next + __popc(idle & lt_mask);
-            if (!have && idx < pool_end) {
-                V3 ro, rd; int avoid; float tmax;
-                io.load(idx, &item, &ro, &rd, &avoid, &tmax);
-                P = ray_pre(ro, rd);
-                avoid_slot = avoid >= 0 ? S.slot_of[avoid] : -1;
-                best = ANYHIT ? fminf(tmax, PTB_INF) : PTB_INF;
-                cull = best + best * PTB_CULL_GUARD;
-                ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-                sp = 0; cur_near = 0.0f; Q.clear();
-                float nr;
-                if (COUNT) { C.boxes++; nrays++; }
-                // the root's own box (the reference pops and tests it first)
-                cur = slab_fast(S.root_lo[0], S.root_lo[1], S.root_lo[2], S.root_hi[0], S.root_hi[1], S.root_hi[2], P, &nr) ? 0 : -1;
-                have = true;
-            }
-            pool_next = min(pool_next + __popc(idle), pool_end);
-        }
-        // ---- bookkeeping: culled current node -> pop; nothing left -> the ray is finished ---------------------------------------------
-        if (have) {
-            if (cur >= 0 && cur_near > cull) cur = -1;                   // the best hit improved since this node was chosen
-            if (cur < 0) {
-                while (sp > 0) {
-                    --sp;
-                    if (!(stack_near[sp] > cull)) { cur = stack_id[sp]; cur_near = stack_near[sp]; break; }
-                }
-                if (cur < 0 && Q.count == 0) {
-                    if (!ANYHIT && ret.hit) ret.index = S.leaf[ret.slot];
-                    io.store(item, ret);
-                    have = false;
-                }
-            }
-        }
-        const bool node_ok = have && cur >= 0 && Q.count <= PTB_PQ - 2;
-        const bool leaf_ok = have && Q.count > 0;
+        // a lane can take a node step if it has a node (current or stacked) and room for two more pending leaves; a leaf step if
+        // a leaf is pending.  A lane with neither is idle: finished (result not stored yet) or never started.
+        const bool node_ok = (cur != -1 || sp > 0) && q_count <= PTB_PQ - 2;
+        const bool leaf_ok = q_count > 0;
         const unsigned mn = __ballot_sync(FULL, node_ok), ml = __ballot_sync(FULL, leaf_ok);
-        if ((mn | ml) == 0u) {
-            if (exhausted && __ballot_sync(FULL, have) == 0u) break;
+        const unsigned idle = ~(mn | ml);
+        if (!exhausted && (__popc(idle) >= PTB_FETCH_MIN || idle == FULL)) {
+            // ---- idle lanes store their result and take the next staged records ----------------------------------------------------------
+            if (!tile_ready) { cp_async_wait<1>(); __syncwarp(); tile_ready = true; }     // the older of the two groups in flight has landed
+            const int nv = cur_buf == 0 ? tile_n0 : tile_n1;
+            if (nv == 0) exhausted = true;                                                 // tiles are handed out in order: nothing is left
+            const bool me = (idle >> lane) & 1u;
+            if (me && item >= 0) { io.store(item, ret, contrib); item = -1; }
+            const int k = tile_pos + __popc(idle & lt_mask);
+            if (me && k < nv) {
+                float4 r[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) r[j] = s_tile[warp][cur_buf][j][k];
+                RayIn in; in.c = v3s(0.0f);
+                io.decode(r, &in);
+                if (ray_is_special(in.ro, in.rd)) {
+                    special_list[atomicAdd(special_count, 1)] = (cur_buf == 0 ? tile_base0 : tile_base1) + k;    // traced by k_trace_simple<1> afterwards (rare)
+                } else {
+                    if (COUNT) nrays++;
+                    item = in.item; avoid_slot = in.avoid_slot; contrib = in.c;
+                    R = ray_cons(in.ro, in.rd);
+                    best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
+                    cull = best + best * PTB_CULL_GUARD;
+                    ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
+                    sp = 0; cur_near = 0.0f; q_head = 0; q_count = 0;
+                    cur = 0;            // the root: its own box is implied by its descendants' boxes (monotone slab test); not `sure`
+                }
+            }
+            tile_pos = min(tile_pos + __popc(idle), nv);
+            if (tile_pos >= nv && !exhausted) {        // tile consumed: switch to the prefetched one and refill this buffer
+                __syncwarp();
+                fill(cur_buf);
+                cur_buf ^= 1; tile_pos = 0; tile_ready = false;
+            }
             continue;
         }
-        if (mn != 0u && __popc(mn) > __popc(ml)) {
-            // ---- node step: one 64-byte node, both children's exact slab tests (all participating lanes run the same code) -----------------
+        if ((mn | ml) == 0u) break;                    // exhausted and nothing in flight
+        if (__popc(mn) > __popc(ml)) {
+            // ---- node step: one 64-byte node, both children's conservative slab tests ---------------------------------------------------------
             if (node_ok) {
-                const Node64 N = S.nodes[cur];
-                if (COUNT) { C.nodes++; C.boxes += 2; }
-                const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
-                float n0, n1;
-                const bool h0 = slab_fast(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, P, &n0);
-                const bool h1 = slab_fast(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, P, &n1);
-                // leaves are always tested (no box predicate in the reference) unless their bounds are entered beyond the cull distance
-                const bool leaf0 = c0 < n, leaf1 = c1 < n;
-                if (leaf0 && c0 != avoid_slot && !(h0 && n0 > cull)) Q.push(c0, h0 ? n0 : 0.0f);
-                if (leaf1 && c1 != avoid_slot && !(h1 && n1 > cull)) Q.push(c1, h1 ? n1 : 0.0f);
-                const bool d0 = !leaf0 && h0 && !(n0 > cull), d1 = !leaf1 && h1 && !(n1 > cull);
-                if (d0 && d1) {
-                    const bool first1 = !(n0 < n1);      // nearer first; equal entry distance: child1 first like the reference
-                    if (sp < PTB_STACK) { stack_id[sp] = (first1 ? c0 : c1) - n; stack_near[sp] = first1 ? n0 : n1; sp++; }
-                    if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
-                    cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
-                } else if (d0) { cur = c0 - n; cur_near = n0; }
-                else if (d1) { cur = c1 - n; cur_near = n1; }
-                else cur = -1;
+                if (cur == -1) {                        // pop (the reload of `tos` is not consumed before the next pop)
+                    cur = (int)(unsigned)tos; cur_near = __int_as_float((int)(tos >> 32));
+                    --sp;
+                    tos = stack[sp];
+                }
+                if (cur_near > cull) cur = -1;          // entered beyond the best hit found since it was pushed / chosen
+                else {
+                    const bool cur_sure = ((unsigned)cur & SURE_BIT) != 0u;
+                    const int ci = (int)((unsigned)cur & ~SURE_BIT);
+                    Node64 N;
+                    if (SMEM) { N.a = s_node[ci]; N.b = s_node[(n - 1) + ci]; N.c = s_node[2 * (n - 1) + ci]; N.d = s_node[3 * (n - 1) + ci]; }
+                    else N = S.nodes[ci];
+                    if (COUNT) { C.nodes++; C.boxes += 2; }
+                    const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
+                    float n0, n1; bool s0, s1;
+                    const bool h0 = slab_cons2(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, R, &n0, &s0);
+                    const bool h1 = slab_cons2(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, R, &n1, &s1);
+                    const bool leaf0 = c0 < n, leaf1 = c1 < n;
+                    const bool in0 = !(n0 > cull), in1 = !(n1 > cull);
+                    // a leaf is a candidate whenever its parent (this node) was reached; its own bounds only allow the distance cull.
+                    // It inherits this node's `sure` flag: this node's box is its gate.
+                    const bool p0 = leaf0 && c0 != avoid_slot && (in0 || !h0);
+                    const bool p1 = leaf1 && c1 != avoid_slot && (in1 || !h1);
+                    const unsigned sure_bit = cur_sure ? SURE_BIT : 0u;
+                    if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = (int)((unsigned)c0 | sure_bit); s_qnear[k][threadIdx.x] = h0 ? n0 : 0.0f; q_count++; }
+                    if (p1) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = (int)((unsigned)c1 | sure_bit); s_qnear[k][threadIdx.x] = h1 ? n1 : 0.0f; q_count++; }
+                    const bool d0 = !leaf0 && h0 && in0, d1 = !leaf1 && h1 && in1;
+                    const int e0 = (int)((unsigned)(c0 - n) | (s0 ? SURE_BIT : 0u)), e1 = (int)((unsigned)(c1 - n) | (s1 ? SURE_BIT : 0u));
+                    const bool first1 = !(n0 < n1);     // nearer first
+                    if (d0 && d1) {
+                        stack[sp] = tos;                // slot 0 receives garbage when sp == 0 (never read back as an entry)
+                        tos = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)(first1 ? e0 : e1);
+                        sp++;                           // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
+                        if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
+                        cur = first1 ? e1 : e0; cur_near = first1 ? n1 : n0;
+                    } else if (d0) { cur = e0; cur_near = n0; }
+                    else if (d1) { cur = e1; cur_near = n1; }
+                    else cur = -1;
+                }
             }
         } else {
             // ---- leaf step: the oldest pending triangle of every lane that has one -----------------------------------------------------------
             if (leaf_ok) {
-                int slot; float lnear;
-                Q.pop(&slot, &lnear);
+                const unsigned qs = (unsigned)s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
+                q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
+                const int slot = (int)(qs & ~SURE_BIT);
                 if (!(lnear > cull)) {
-                    const Tri64 T = S.tris[slot];
+                    Tri64 T;
+                    if (SMEM) { T.a = s_tri[slot]; T.b = s_tri[n + slot]; T.c = s_tri[2 * n + slot]; T.d = s_tri[3 * n + slot]; }
+                    else T = S.tris[slot];
                     if (COUNT) C.tris++;
                     float dep, s, t;
-                    if (tri_fast(T, P.o, P.d, best, &dep, &s, &t)) {
-                        if (ANYHIT) {
-                            if (dep < PTB_INF) {                              // occluded: done with this ray
-                                ret.hit = 1; ret.depth = dep; ret.u = s; ret.v = t; ret.slot = slot; ret.index = S.leaf[slot];
-                                io.store(item, ret);
-                                have = false;
-                            }
-                        } else if (dep < ret.depth || (ret.hit && slot > ret.slot)) {     // here dep <= best == ret.depth
+                    if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
+                        // here dep <= best; the candidate counts only if the reference reaches it: its gate passes the exact slab test
+                        // (known from the conservative bounds unless the ray grazes the gate)
+                        const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+                        if (better && ((qs & SURE_BIT) != 0u || gate_passes(S, S.gate[slot], R.o, R.d))) {
                             ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
-                            best = dep; cull = dep + dep * PTB_CULL_GUARD;
+                            ret.index = S.leaf[slot];                         // face id: only read when the ray is stored
+                            if (ANYHIT) { cur = -1; sp = 0; q_count = 0; }    // occluded: done with this ray (stored when the lane is refilled)
+                            else { best = dep; cull = dep + dep * PTB_CULL_GUARD; }
                         }
                     }
                 }
             }
         }
     }
+    if (item >= 0) io.store(item, ret, contrib);
+    cp_async_wait<0>();
     flush_counters<COUNT>(C, nrays, ANYHIT, ctr);
 }

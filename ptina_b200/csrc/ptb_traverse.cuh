@@ -31,6 +31,7 @@ struct TraceScene {
     const Tri64* __restrict__ tris;      // [n]  by leaf slot
     const int* __restrict__ leaf;        // [n]  slot -> face id      (lbvh.py:55)
     const int* __restrict__ slot_of;     // [n]  face id -> slot      (inverse of leaf, proper trees only)
+    const int* __restrict__ gate;        // [n]  slot -> internal node whose child the leaf is (its box gates the triangle test)
     // reference arrays (lbvh.py:50-59) for the literal traversal
     const float* __restrict__ bmin;      // [n-1][3]
     const float* __restrict__ bmax;      // [n-1][3]
@@ -110,6 +111,70 @@ PTB_D bool slab_fast(float lox, float loy, float loz, float hix, float hiy, floa
     return !(tnear > tfar);
 }
 
+// ---- conservative slab test (production traversal) ------------------------------------------------------------------------------
+// The reference's slab test is monotone in the box: for B' inside B (lo' >= lo, hi' <= hi componentwise) every f32 step of
+// Box.intersect -- RN(p - o), RN(x / d), the swap, min/max -- is a monotone function of the plane coordinate p, so the t-interval
+// of B' is contained in the t-interval of B axis by axis (and `origin inside the slab` of B' implies it for B on a parallel
+// axis).  Hence  hit(B') => hit(B)  EXACTLY, in f32.  Internal boxes are exact min/max unions of their children, so along a
+// root-to-leaf chain "every ancestor's box passes" is equivalent to "the box of the leaf's parent passes": the reference tests a
+// triangle iff the exact slab test of its parent's box (its GATE) passes.  The production traversal therefore only needs box
+// tests that never reject a box the exact test accepts; it finds candidate triangles with the cheap test below (1 FMA per
+// plane) and runs the exact division test once, on the gate of a triangle that is about to be accepted (gate_passes).
+//
+// Error bound.  Reference: t_ref = RN(RN(p - o) / d) = T(1+e1)(1+e2), T = (p-o)/d, |e| <= u = 2^-24.
+// Here: r = RN(1/d), c = RN(o*r), t = RN(p*r - c) (one FMA) = (T(1+e3) - (o/d)(1+e3)e4)(1+e5).
+// => |t - t_ref| <= 4.1u|t| + 1.1u|c|.  With A = max_axis |c| the bounds  L(t) = t - 8u|t| - 4uA  <=  t_ref  <=  U(t) = t + 8u|t| + 4uA
+// are monotone in t, so they commute with the per-axis min/max and with the clamps (0 and 1e6 are exact):
+//   tnear_ref >= lb := max(0, near)(1 - 8u) - a2,   tfar_ref <= ub := far + 8u|far| + a2',   a2 + a2' folded into lb (a2 = 8uA + 1e-30;
+// the 1e-30 covers results in the denormal range).  The exact test passes only if tnear_ref <= tfar_ref, hence only if lb <= ub.
+// Comparisons are written so that a NaN (overflowing coordinates) counts as "hit".  Rays with an axis-parallel component,
+// non-finite or huge components are not handled here: the kernel sends them through trace_ordered (exact tests).
+#define PTB_CONS_KAPPA 4.76837158203125e-7f      /* 2^-21 = 8u */
+struct RayCons { V3 o, d, r, nc; float a2; };
+PTB_D bool ray_is_special(V3 o, V3 d) {
+    const float big = 1e30f;
+    bool ok = fabsf(d.x) >= PTB_EPS && fabsf(d.y) >= PTB_EPS && fabsf(d.z) >= PTB_EPS && fabsf(d.x) <= big && fabsf(d.y) <= big && fabsf(d.z) <= big &&
+              fabsf(o.x) <= big && fabsf(o.y) <= big && fabsf(o.z) <= big;
+    return !ok;            // NaNs fail every comparison above
+}
+PTB_D RayCons ray_cons(V3 o, V3 d) {
+    RayCons R; R.o = o; R.d = d;
+    R.r = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    R.nc = mk3(-(o.x * R.r.x), -(o.y * R.r.y), -(o.z * R.r.z));
+    R.a2 = __fmaf_rn(fmaxf(fmaxf(fabsf(R.nc.x), fabsf(R.nc.y)), fabsf(R.nc.z)), PTB_CONS_KAPPA, 1e-30f);
+    return R;
+}
+// *lb: lower bound of the reference's tnear for this box (valid whether or not the box is hit); returns false only if the
+// reference's test certainly fails.
+PTB_D bool slab_cons(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayCons& R, float* lb) {
+    const float x1 = __fmaf_rn(lox, R.r.x, R.nc.x), x2 = __fmaf_rn(hix, R.r.x, R.nc.x);
+    const float y1 = __fmaf_rn(loy, R.r.y, R.nc.y), y2 = __fmaf_rn(hiy, R.r.y, R.nc.y);
+    const float z1 = __fmaf_rn(loz, R.r.z, R.nc.z), z2 = __fmaf_rn(hiz, R.r.z, R.nc.z);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
+    const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -R.a2);
+    const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
+    *lb = l;
+    return !(l > ub);
+}
+// The same, plus *sure = the reference's test CERTAINLY passes: an upper bound of its tnear is <= a lower bound of its tfar
+// (tnear_ref <= tn(1+8u) + a2,  tfar_ref >= tf - 8u|tf|, a2 carrying both absolute terms).  A triangle whose gate is `sure` needs
+// no exact gate test; only rays grazing the gate (difference within ~1e-6 relative) are ambiguous.
+PTB_D bool slab_cons2(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayCons& R, float* lb, bool* sure) {
+    const float x1 = __fmaf_rn(lox, R.r.x, R.nc.x), x2 = __fmaf_rn(hix, R.r.x, R.nc.x);
+    const float y1 = __fmaf_rn(loy, R.r.y, R.nc.y), y2 = __fmaf_rn(hiy, R.r.y, R.nc.y);
+    const float z1 = __fmaf_rn(loz, R.r.z, R.nc.z), z2 = __fmaf_rn(hiz, R.r.z, R.nc.z);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
+    const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -R.a2);
+    const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
+    const float hi_n = __fmaf_rn(tn, 1.0f + PTB_CONS_KAPPA, R.a2);
+    const float lo_f = __fmaf_rn(fabsf(tf), -PTB_CONS_KAPPA, tf);
+    *lb = l;
+    *sure = hi_n <= lo_f;              // false on NaN
+    return !(l > ub);
+}
+
 // geometries.py:117-148 on the packed record, literal (true divisions).  Returns hit; depth/s/t as the reference.
 PTB_D bool tri_ref(const Tri64& T, V3 ro, V3 rd, float* depth, float* s_out, float* t_out) {
     V3 v0 = mk3(T.a.x, T.a.y, T.a.z), u = mk3(T.b.x, T.b.y, T.b.z), v = mk3(T.c.x, T.c.y, T.c.z), nrm = mk3(T.d.x, T.d.y, T.d.z);
@@ -137,6 +202,9 @@ PTB_D bool tri_fast(const Tri64& T, V3 ro, V3 rd, float tlimit, float* depth, fl
     float b = dot(nrm, rd);
     if (!(fabsf(b) >= PTB_EPS)) return false;
     float a = -dot(nrm, ro - v0);
+    // RN(a / b) > 0 needs a != 0 and equal signs: decided without the division (which takes its slow path for a == 0 -- common,
+    // the origin lies on the plane of every coplanar neighbour of the surface it left)
+    if (a == 0.0f || ((a < 0.0f) != (b < 0.0f))) return false;
     float r = a / b;
     if (!(r > 0.0f) || r > tlimit) return false;
     V3 u = mk3(T.b.x, T.b.y, T.b.z), v = mk3(T.c.x, T.c.y, T.c.z);
@@ -148,6 +216,12 @@ PTB_D bool tri_fast(const Tri64& T, V3 ro, V3 rd, float tlimit, float* depth, fl
     float t = div_exact(uv * wu - uu * wv, D, rD);
     *s_out = s; *t_out = t; *depth = r;
     return (0.0f <= s && s <= 1.0f) && (0.0f <= t && s + t <= 1.0f);
+}
+
+// The exact gate: Box.intersect (division form) on the box of internal node g, as the reference evaluates it when it pops g.
+PTB_D bool gate_passes(const TraceScene& S, int g, V3 ro, V3 rd) {
+    float nr;
+    return slab_ref(S.bmin[3 * g], S.bmin[3 * g + 1], S.bmin[3 * g + 2], S.bmax[3 * g], S.bmax[3 * g + 1], S.bmax[3 * g + 2], ro, rd, &nr);
 }
 
 // ---- tree/lbvh.py:313-347, literal order ------------------------------------------------------------------

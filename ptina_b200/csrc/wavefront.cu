@@ -18,6 +18,7 @@
 // pure function of the bounce number (2 jitter draws, then 3 NEE + 3 bounce draws per bounce), so no per-path
 // generator state is carried.
 #include <cstdio>
+#include <cstdlib>
 #include "ptb_internal.h"
 #include "ptb_trace_kernel.cuh"
 
@@ -53,7 +54,8 @@ struct Rng {
 };
 
 // ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
-PTB_D void block_append(bool flag, int value, int* __restrict__ queue, int* counter, int* s_warp, int* s_base) {
+// returns the queue position reserved for this thread (-1 if !flag)
+PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     unsigned m = __ballot_sync(0xffffffffu, flag);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int rank = __popc(m & ((1u << lane) - 1u));
@@ -66,8 +68,9 @@ PTB_D void block_append(bool flag, int value, int* __restrict__ queue, int* coun
         *s_base = tot ? atomicAdd(counter, tot) : 0;
     }
     __syncthreads();
-    if (flag) queue[*s_base + s_warp[w] + rank] = value;
+    int pos = flag ? *s_base + s_warp[w] + rank : -1;
     __syncthreads();
+    return pos;
 }
 
 // ---- sampling/sobol.py:99-105 in closed form: X_k = XOR_{b in gray(k)} V[b+1];  P = X / 2^32 (sobol.py:19-29) ---------
@@ -84,18 +87,21 @@ __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, 
 }
 
 __global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
+__global__ void k_ctrl_special(Ctrl* c) { c->special[0] = 0; c->special[1] = 0; }
 __global__ void k_ctrl_tap(Ctrl* c, int m) { c->pad[0] = m; c->pad[1] = 0; }
 __global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
 
 // ---- path.py:85-93 do_render (first half) / brute.py:66-73 -----------------------------------------------------------
-__global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ P, const float* __restrict__ sobolP, int dim, FrameMap fm, int nsamp,
-                                                PathState st, int* __restrict__ queue, Ctrl* ctrl, DevCounters* ctr) {
+// renorm: path_trace normalises the (already unit) camera direction again before intersecting (path.py:28); PreviewEngine does not
+__global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ P, const float* __restrict__ sobolP, int dim, FrameMap fm, int nsamp, int renorm,
+                                                PathState st, RayQueue xq, Ctrl* ctrl, DevCounters* ctr) {
     __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
     int total = fm.pps * nsamp;
     int rounded = (total + BLK - 1) / BLK * BLK;
     for (int p0 = blockIdx.x * BLK; p0 < rounded; p0 += gridDim.x * BLK) {
         int p = p0 + threadIdx.x;
         bool live = false;
+        V3 ro = v3s(0.0f), rd = v3s(0.0f);
         if (p < total) {
             int s = p / fm.pps, q = p - s * fm.pps;
             int x, y;
@@ -105,15 +111,19 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
                 float dx = rng.draw(0), dy = rng.draw(1);
                 float fx = ((float)x + dx) / (float)fm.nx * 2.0f - 1.0f;
                 float fy = ((float)y + dy) / (float)fm.ny * 2.0f - 1.0f;
-                V3 ro, rd;
                 camera_generate(P, fx, fy, &ro, &rd);
-                st.ray_o[p] = make_float4(ro.x, ro.y, ro.z, 0.0f);                         // last_brdf_pdf = 0
-                st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));           // avoid = -1
+                st.ray_o[p] = make_float4(ro.x, ro.y, ro.z, 0.0f);
+                st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, 0.0f);
                 st.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));              // depth = 0
-                st.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                st.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                         // last_brdf_pdf = 0
             }
         }
-        block_append(live, p, queue, &ctrl->n_in, s_warp, &s_base);
+        int pos = block_append(live, &ctrl->n_in, s_warp, &s_base);
+        if (live) {
+            if (renorm) rd = normalized(rd);
+            xq.o[pos] = make_float4(ro.x, ro.y, ro.z, __int_as_float(p));
+            xq.d[pos] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));                 // avoid = -1
+        }
     }
     if (ctr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->paths, (unsigned long long)nsamp * fm.nx * fm.ny);
 }
@@ -138,21 +148,24 @@ PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict_
 // ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
 template <int ENGINE>
 __global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
-                                               const int* __restrict__ mtlids, const float* __restrict__ rngtab, int dim, int rng_stride, FrameMap fm,
-                                               PathState st, const int* __restrict__ q_in, int* __restrict__ q_out, int* __restrict__ q_shadow, Ctrl* ctrl) {
+                                               const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
+                                               FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
     __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
     const int count = ctrl->n_in;
     const int rounded = (count + BLK - 1) / BLK * BLK;
     for (int i0 = blockIdx.x * BLK; i0 < rounded; i0 += gridDim.x * BLK) {
         int idx = i0 + threadIdx.x;
         bool alive = false, want_shadow = false;
-        int p = -1;
+        int p = -1, avoid_slot = -1;
+        V3 next_o = v3s(0.0f), next_d = v3s(0.0f), sh_dir = v3s(0.0f), sh_contrib = v3s(0.0f);
+        float sh_dis = 0.0f;
         if (idx < count) {
-            p = q_in[idx];
-            float4 o4 = st.ray_o[p], d4 = st.ray_d[p], h4 = st.hit[p], t4 = st.thr[p], r4 = st.result[p];
+            float4 o4 = q_in.o[idx], d4 = q_in.d[idx];
+            p = __float_as_int(o4.w);
+            float4 h4 = st.hit[p], t4 = st.thr[p], r4 = st.result[p];
             V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
             V3 thr = mk3(t4.x, t4.y, t4.z), result = mk3(r4.x, r4.y, r4.z);
-            float last_pdf = o4.w;
+            float last_pdf = r4.w;
             int depth = __float_as_int(t4.w) + 1;                       // path.py:26 depth += 1
             int hit_index = __float_as_int(h4.w);
             bool hit = hit_index >= 0;
@@ -176,6 +189,7 @@ __global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P
             if (!hit) {
                 result = result + thr * world_at(P, texels, rd);        // path.py:37-39
             } else {
+                avoid_slot = __ldg(&slot_of[hit_index]);
                 V3 hitpos, normal; float tu, tv; int mtlid;
                 shading_frame(verts, mtlids, hit_index, h4.y, h4.z, ro, rd, h4.x, &hitpos, &normal, &tu, &tv, &mtlid);
                 Disney mat = material_get(P, texels, mtlid, tu, tv);
@@ -197,8 +211,7 @@ __global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P
                         // a contribution that is exactly zero (light sample below the horizon, black throughput) adds nothing whether or
                         // not the shadow ray is blocked, so the ray is not traced; NaNs compare unequal and still go through
                         if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
-                            st.sh_d[p] = make_float4(li.dir.x, li.dir.y, li.dir.z, li.dis);
-                            st.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+                            sh_dir = li.dir; sh_dis = li.dis; sh_contrib = contrib;
                             want_shadow = true;
                         }
                     }
@@ -209,17 +222,29 @@ __global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P
                 // path.py:58-62 / brute.py:56-60
                 BSDFSample bs = disney_bounce(mat, normal, sign, wi, mk3(rng.draw(c0), rng.draw(c0 + 1), rng.draw(c0 + 2)));
                 thr = thr * bs.color;
-                st.ray_o[p] = make_float4(hitpos.x, hitpos.y, hitpos.z, bs.pdf);
-                st.ray_d[p] = make_float4(bs.outdir.x, bs.outdir.y, bs.outdir.z, __int_as_float(hit_index));   // avoid = hit.index
+                last_pdf = bs.pdf;                                         // path.py:61
                 st.thr[p] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
                 // loop condition path.py:25 / brute.py:35
                 if (ENGINE == PTB_ENGINE_PATH) alive = depth < 5 && any_gt(thr, 0.0f) && any_ne0(bs.outdir);
                 else alive = depth < 5 && any_gt(thr, PTB_EPS);
+                next_o = hitpos;
+                if (alive) next_d = normalized(bs.outdir);                 // path.py:28  r.d = r.d.normalized() at the top of the next iteration
             }
-            st.result[p] = make_float4(result.x, result.y, result.z, 0.0f);
+            st.result[p] = make_float4(result.x, result.y, result.z, last_pdf);
         }
-        block_append(alive, p, q_out, &ctrl->n_out, s_warp, &s_base);
-        if (ENGINE == PTB_ENGINE_PATH) block_append(want_shadow, p, q_shadow, &ctrl->n_shadow, s_warp, &s_base);
+        int pos = block_append(alive, &ctrl->n_out, s_warp, &s_base);
+        if (alive) {
+            q_out.o[pos] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
+            q_out.d[pos] = make_float4(next_d.x, next_d.y, next_d.z, __int_as_float(avoid_slot));   // avoid = hit.index (as its leaf slot)
+        }
+        if (ENGINE == PTB_ENGINE_PATH) {
+            int ps = block_append(want_shadow, &ctrl->n_shadow, s_warp, &s_base);
+            if (want_shadow) {
+                q_shadow.o[ps] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
+                q_shadow.d[ps] = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, sh_dis);
+                q_shadow.c[ps] = make_float4(sh_contrib.x, sh_contrib.y, sh_contrib.z, __int_as_float(avoid_slot));
+            }
+        }
     }
 }
 
@@ -289,6 +314,17 @@ __global__ void __launch_bounds__(BLK) k_resolve(const float4* __restrict__ film
 }
 
 // ---- taps ----------------------------------------------------------------------------------------------------------------------------------
+// flat ray arrays of ptb_intersect / ptb_occluded -> queue records (directions are used as given, like LinearBVH.intersect)
+__global__ void __launch_bounds__(BLK) k_pack_tap(const float* __restrict__ rays, const int* __restrict__ avoid, const float* __restrict__ dis,
+                                                  const int* __restrict__ slot_of, int nfaces, int m, RayQueue q) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    int av = avoid ? avoid[i] : -1;
+    int slot = (av >= 0 && av < nfaces) ? slot_of[av] : -1;
+    q.o[i] = make_float4(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2], __int_as_float(i));
+    q.d[i] = make_float4(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5], dis ? dis[i] : __int_as_float(slot));
+    if (dis) q.c[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(slot));
+}
 __global__ void __launch_bounds__(BLK) k_gather_primary(FrameMap fm, PathState st, float* rays, int* hit, float* depth, int* index, float* uv, int which) {
     int q = blockIdx.x * BLK + threadIdx.x;
     if (q >= fm.pps) return;
@@ -412,7 +448,7 @@ __global__ void __launch_bounds__(BLK) k_mlt_reset(float* Xold, float4* Lold, in
 }
 // mltpath.py:56-74: mutate, then camera ray from the first two dims
 __global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restrict__ P, const float* __restrict__ Xold, float* __restrict__ Xnew, int nchains, int chain_first,
-                                                    uint64_t seed, uint32_t iter, float lsp, float sigma, PathState st, int* __restrict__ queue, Ctrl* ctrl, DevCounters* ctr) {
+                                                    uint64_t seed, uint32_t iter, float lsp, float sigma, PathState st, RayQueue xq, Ctrl* ctrl, DevCounters* ctr) {
     int i = blockIdx.x * BLK + threadIdx.x;
     if (i >= nchains) return;
     Philox g; g.init(seed, (uint32_t)(chain_first + i), iter);
@@ -421,11 +457,11 @@ __global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restric
     else { for (int j = 0; j < 32; j++) xn[j] = pymodf1(xo[j] + sigma * normaldist(g.next())); }
     V3 ro, rd;
     camera_generate(P, xn[0] * 2.0f - 1.0f, xn[1] * 2.0f - 1.0f, &ro, &rd);
-    st.ray_o[i] = make_float4(ro.x, ro.y, ro.z, 0.0f);
-    st.ray_d[i] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));
     st.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
     st.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    queue[i] = i;
+    rd = normalized(rd);                                                                // path.py:28
+    xq.o[i] = make_float4(ro.x, ro.y, ro.z, __int_as_float(i));
+    xq.d[i] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));
     if (i == 0) { ctrl->n_in = nchains; if (ctr) atomicAdd(&ctr->paths, (unsigned long long)nchains); }
 }
 // mltpath.py:47-52 splat + 75-81 accept/reject
@@ -487,12 +523,32 @@ static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int poli
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     cudaStream_t st = c->stream;
     if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
-        if (c->counting) k_trace_ref<IO, true><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
-        else k_trace_ref<IO, false><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        if (c->counting) k_trace_simple<IO, 0, true><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        else k_trace_simple<IO, 0, false><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+    } else if (policy == PTB_TRAVERSE_ORDERED_EXACT) {
+        if (c->counting) k_trace_simple<IO, 1, true><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        else k_trace_simple<IO, 1, false><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
     } else {
-        int blocks = IO::kAnyHit ? c->blocks_shadow : c->blocks_extend;
-        if (c->counting) k_trace<IO, true><<<blocks, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
-        else k_trace<IO, false><<<blocks, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
+        int* sp_count = &c->d_ctrl->special[0]; int* sp_cursor = &c->d_ctrl->special[1];
+        constexpr int K = IO::K;
+        const size_t resident = TraceSmem<K, PTB_TRACE_BLK_S>::fixed + TraceSmem<K, PTB_TRACE_BLK_S>::bvh(S.n);
+        if (resident <= (size_t)c->smem_optin && !c->no_resident_bvh) {
+            // the packed BVH fits in shared memory: one CTA per SM keeps it resident
+            auto kern = c->counting ? k_trace<IO, true, PTB_TRACE_BLK_S, true> : k_trace<IO, false, PTB_TRACE_BLK_S, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, resident, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
+        } else {
+            int blocks = IO::kAnyHit ? c->blocks_shadow : c->blocks_extend;
+            auto kern = c->counting ? k_trace<IO, true, PTB_TRACE_BLK, false> : k_trace<IO, false, PTB_TRACE_BLK, false>;
+            kern<<<blocks, PTB_TRACE_BLK, TraceSmem<K, PTB_TRACE_BLK>::fixed, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
+        }
+        // rays set aside by the production kernel (axis-parallel / non-finite): exact-test kernel over the (usually empty) list;
+        // its last action resets the list for the next launch
+        ListedIO<IO> lio{io, c->d_specialq};
+        if (c->counting) k_trace_simple<ListedIO<IO>, 1, true><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
+        else k_trace_simple<ListedIO<IO>, 1, false><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
+        k_ctrl_special<<<1, 1, 0, st>>>(c->d_ctrl);
+        c->launches += 2;
     }
     c->launches++;
 }
@@ -526,21 +582,25 @@ int ptb_stage_collect(ptb_ctx* c) {
 
 int ptb_wf_init(ptb_ctx* c) {
     int64_t np = c->max_paths;
-    float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result, &c->st.sh_d, &c->st.sh_c};
+    float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result,
+                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
-    PTB_CUDA(cudaMalloc(&c->d_queue[0], sizeof(int) * np));
-    PTB_CUDA(cudaMalloc(&c->d_queue[1], sizeof(int) * np));
-    PTB_CUDA(cudaMalloc(&c->d_shadowq, sizeof(int) * np));
+    PTB_CUDA(cudaMalloc(&c->d_specialq, sizeof(int) * np));
     PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
+    PTB_CUDA(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
     PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
     int occ = 0;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ExtendIO, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ExtendIO, false, PTB_TRACE_BLK, false>, PTB_TRACE_BLK, TraceSmem<2, PTB_TRACE_BLK>::fixed));
     c->blocks_extend = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ShadowIO, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ShadowIO, false, PTB_TRACE_BLK, false>, PTB_TRACE_BLK, TraceSmem<3, PTB_TRACE_BLK>::fixed));
     c->blocks_shadow = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_ref<ExtendIO, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
+    c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
     c->blocks_ref = c->sm_count * (occ > 0 ? occ : 4);
     c->blocks_generic = c->sm_count * 8;
     return 0;
@@ -582,16 +642,16 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     int cur = 0;
     for (int depth = 1; depth <= 5; depth++) {
         ptb_stage_begin(c, ST_EXTEND);
-        { ExtendIO io; io.st = c->st; io.queue = c->d_queue[cur]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+        { ExtendIO io{c->xq[cur].o, c->xq[cur].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
         ptb_stage_end(c);
         ptb_stage_begin(c, ST_SHADE);
-        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, rngtab, dim, rng_stride, fm, c->st,
-                                                            c->d_queue[cur], c->d_queue[cur ^ 1], c->d_shadowq, c->d_ctrl);
+        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
+                                                            c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
         ptb_stage_end(c);
         c->launches += 1;
         if (ENGINE == PTB_ENGINE_PATH) {
             ptb_stage_begin(c, ST_SHADOW);
-            { ShadowIO io; io.st = c->st; io.queue = c->d_shadowq; launch_trace(c, S, io, policy, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow); }
+            { ShadowIO io{c->sq.o, c->sq.d, c->sq.c, c->st.result}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow); }
             ptb_stage_end(c);
         }
         k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
@@ -617,7 +677,7 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
             ptb_stage_begin(c, ST_RAYGEN);
             k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
             k_mlt_raygen<<<nblk(n), BLK, 0, st>>>(c->d_params, c->d_Xold, c->d_Xnew, n, c->mlt_first, c->mlt_seed, c->mlt_iter, c->mlt_lsp, c->mlt_sigma,
-                                                  c->st, c->d_queue[0], c->d_ctrl, ctr);
+                                                  c->st, c->xq[0], c->d_ctrl, ctr);
             ptb_stage_end(c);
             c->launches += 2;
             if (run_bounces<PTB_ENGINE_PATH>(c, c->d_Xnew, 0, 32, fm)) return 1;
@@ -640,14 +700,14 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
         ptb_stage_begin(c, ST_RAYGEN);
         if (ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
         k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
-        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, c->st, c->d_queue[0], c->d_ctrl, ctr);
+        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, engine != PTB_ENGINE_PREVIEW, c->st, c->xq[0], c->d_ctrl, ctr);
         ptb_stage_end(c);
         c->launches += 2;
         if (engine == PTB_ENGINE_PREVIEW) {
             TraceScene S = ptb_trace_scene(c);
             int policy = ptb_effective_policy(c, c->traversal_request);
             ptb_stage_begin(c, ST_EXTEND);
-            { ExtendIO io; io.st = c->st; io.queue = c->d_queue[0]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+            { ExtendIO io{c->xq[0].o, c->xq[0].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
             ptb_stage_end(c);
             ptb_stage_begin(c, ST_ACCUM);
             size_t pass = (size_t)c->caps.max_filmsize;
@@ -677,13 +737,13 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
     if (ensure_sobolP(c, 1)) return 1;
     if (ptb_wf_sobol_points(c, k, 1, 1, c->d_sobolP)) return 1;
     k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
-    k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, c->st, c->d_queue[0], c->d_ctrl, nullptr);
+    k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, 1, c->st, c->xq[0], c->d_ctrl, nullptr);
     if (rays_dev) k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, rays_dev, nullptr, nullptr, nullptr, nullptr, 0);
     if (hit_dev || depth_dev || index_dev || uv_dev) {
         if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
         TraceScene S = ptb_trace_scene(c);
         int policy = ptb_effective_policy(c, c->traversal_request);
-        { ExtendIO io; io.st = c->st; io.queue = c->d_queue[0]; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+        { ExtendIO io{c->xq[0].o, c->xq[0].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
         k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, nullptr, hit_dev, depth_dev, index_dev, uv_dev, 1);
     }
     c->launches += 4;
@@ -694,12 +754,14 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
 int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev, const float* dis_dev, int m, int policy, int anyhit,
                      int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev) {
     if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
+    if (m > c->max_paths) { ptb_set_error("%d rays exceed the ray queue capacity %lld", m, (long long)c->max_paths); return 1; }
     TraceScene S = ptb_trace_scene(c);
     k_ctrl_tap<<<1, 1, 0, c->stream>>>(c->d_ctrl, m);
-    c->launches++;
+    k_pack_tap<<<nblk(m), BLK, 0, c->stream>>>(rays_dev, avoid_dev, anyhit ? dis_dev : nullptr, c->d_slot_of, c->nfaces, m, c->sq);
+    c->launches += 2;
     int eff = ptb_effective_policy(c, policy);
-    if (anyhit) { TapIO<true> io{rays_dev, avoid_dev, dis_dev, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
-    else { TapIO<false> io{rays_dev, avoid_dev, dis_dev, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
+    if (anyhit) { TapIO<true> io{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
+    else { TapIO<false> io{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
     PTB_CUDA(cudaGetLastError());
     return 0;
 }

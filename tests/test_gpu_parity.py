@@ -76,15 +76,95 @@ def test_secondary_rays_match_reference_order(gpu, name):
     rays = np.concatenate([org, d], 1).astype(np.float32)
     avoid = f.astype(np.int32)
     ref = o.intersect(rays, avoid)
-    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_REFERENCE):
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
         got = gpu.intersect(rays, avoid, policy)
         assert np.array_equal(got['index'], ref['index']), f'policy {policy}: {(got["index"] != ref["index"]).sum()} ids differ'
         h = ref['hit'] == 1
         assert np.array_equal(bits(got['depth'])[h], bits(ref['depth'])[h]) and np.array_equal(bits(got['uv'])[h], bits(ref['uv'])[h])
     dis = np.where(ref['hit'] == 1, ref['depth'] * rng.choice([0.5, 1.0, 1.5], m), 5.0).astype(np.float32)
     want = ((ref['hit'] == 1) & (ref['depth'] <= dis)).astype(np.int32)
-    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_REFERENCE):
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
         assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want)
+
+
+@pytest.mark.parametrize('name', ['cornell_boxes', 'cornell_monkey', 'mega_small'])
+def test_adversarial_rays_match_reference_order(gpu, name):
+    """Rays built to stress the conservative box test + exact gate test of the production kernel: axis-parallel and nearly
+    axis-parallel directions (|d| around the 1e-6 threshold of Box.intersect), rays aimed exactly at triangle vertices / edge
+    midpoints / box corners (grazing the gates), origins on box planes, far-away origins, zero and non-finite directions.  Every
+    policy must reproduce the oracle's literal traversal bit for bit."""
+    sc, o = load(gpu, name, SMALL[name])
+    rng = np.random.default_rng(17)
+    tree = o.export_tree()
+    verts = np.asarray(sc['vertices'], np.float32)[:, :3].reshape(-1, 3, 3)
+    nf = verts.shape[0]
+    rays, avoid = [], []
+
+    def add(org, d, av=None):
+        org = np.asarray(org, np.float32).reshape(-1, 3); d = np.asarray(d, np.float32).reshape(-1, 3)
+        rays.append(np.concatenate([org, np.broadcast_to(d, org.shape) if d.shape[0] == 1 else d], 1))
+        avoid.append(np.full(org.shape[0], -1, np.int32) if av is None else np.asarray(av, np.int32))
+
+    m = 4000
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    ctr, ext = (lo + hi) / 2, (hi - lo)
+    # 1. axis-parallel and almost axis-parallel directions
+    for axis in range(3):
+        for tiny in (0.0, 5e-7, 9.99e-7, 1e-6, 1.01e-6, 1e-5, -5e-7, -1.5e-6):
+            d = rng.normal(size=(m // 8, 3)).astype(np.float32)
+            d[:, axis] = tiny
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            d[:, axis] = tiny
+            org = (ctr + (rng.uniform(-0.7, 0.7, (m // 8, 3)) * ext)).astype(np.float32)
+            add(org, d)
+    for axis in range(3):          # exactly along an axis, both signs, from inside and outside
+        for sgn in (1.0, -1.0):
+            d = np.zeros((m // 4, 3), np.float32); d[:, axis] = sgn
+            add((ctr + rng.uniform(-0.8, 0.8, (m // 4, 3)) * ext).astype(np.float32), d)
+    # 2. aimed exactly at vertices, edge midpoints and node-box corners
+    f = rng.integers(0, nf, m)
+    org = (ctr + rng.uniform(-0.45, 0.45, (m, 3)) * ext).astype(np.float32)
+    tgt = verts[f, rng.integers(0, 3, m)]
+    d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    add(org, d)
+    k = rng.integers(0, 3, m)
+    tgt = (verts[f, k] + verts[f, (k + 1) % 3]) * np.float32(0.5)
+    d = tgt - org; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    add(org, d)
+    nb = tree['bmin'].shape[0]
+    j = rng.integers(0, nb, m)
+    pick = rng.integers(0, 2, (m, 3)).astype(bool)
+    tgt = np.where(pick, tree['bmin'][j], tree['bmax'][j]).astype(np.float32)
+    d = tgt - org; d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    add(org, d)
+    # 3. origins exactly on box planes / triangle vertices (with and without avoid), far-away origins
+    org = np.where(pick, tree['bmin'][j], tree['bmax'][j]).astype(np.float32)
+    add(org, _unit(rng, m))
+    add(verts[f, 0], _unit(rng, m), f)
+    add(verts[f, 1], _unit(rng, m))
+    far = (ctr + _unit(rng, m) * np.float32(1e4) * np.linalg.norm(ext)).astype(np.float32)
+    d = (ctr + rng.uniform(-0.5, 0.5, (m, 3)) * ext - far); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    add(far, d)
+    # 4. degenerate directions
+    bad = np.array([[0, 0, 0], [np.nan, 0.3, 0.4], [np.inf, 0, 0], [1e-20, 1e-20, 1e-20], [0, 1, 0], [1e30, 1e30, 1e30], [np.nan] * 3], np.float32)
+    for b in bad:
+        add((ctr + rng.uniform(-0.4, 0.4, (16, 3)) * ext).astype(np.float32), b[None])
+    add(np.full((4, 3), np.nan, np.float32), _unit(rng, 4))
+    rays = np.ascontiguousarray(np.concatenate(rays, 0), np.float32); avoid = np.ascontiguousarray(np.concatenate(avoid, 0))
+    ref = o.intersect(rays, avoid)
+    h = ref['hit'] == 1
+    assert h.sum() > len(h) // 10
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
+        got = gpu.intersect(rays, avoid, policy)
+        bad_i = np.nonzero(got['index'] != ref['index'])[0]
+        assert bad_i.size == 0, f'policy {policy}: {bad_i.size} ids differ, first ray {rays[bad_i[0]]} got {got["index"][bad_i[0]]} want {ref["index"][bad_i[0]]}'
+        assert np.array_equal(got['hit'], ref['hit'])
+        assert np.array_equal(bits(got['depth'])[h], bits(ref['depth'])[h]) and np.array_equal(bits(got['uv'])[h], bits(ref['uv'])[h])
+    with np.errstate(invalid='ignore'):
+        dis = np.where(h, ref['depth'] * rng.choice([0.5, 1.0, 1.0, 1.5], len(h)), 5.0).astype(np.float32)
+        want = (h & (ref['depth'] <= dis)).astype(np.int32)
+    for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
+        assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want), f'policy {policy}: shadow queries differ'
 
 
 def _random_materials(rng, m):
