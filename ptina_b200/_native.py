@@ -67,10 +67,11 @@ def load_library():
     """dlopen the in-tree libptina_b200.so.  Raises (never falls back) if it is missing."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            raise NativeError(f'{_SO} is missing: build it with `python -m ptina_b200.build` '
+        so = os.environ.get('PTINA_B200_LIB', _SO)        # tuning builds (ptina_b200/build.py --out=...); still no CPU fallback
+        if not os.path.exists(so):
+            raise NativeError(f'{so} is missing: build it with `python -m ptina_b200.build` '
                               '(ptina_b200 has no CPU fallback)')
-        L = ctypes.CDLL(_SO)
+        L = ctypes.CDLL(so)
         L.ptb_last_error.restype = ctypes.c_char_p
         for name in SYMBOLS:
             fn = getattr(L, name)

@@ -32,9 +32,12 @@ def stale():
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: tuning variants (`-DNAME=value` ... into another .so, selected at run time with PTINA_B200_LIB)."""
+    if not force and not stale() and not defines and out is None:
         return SO
+    out = out or SO
+    tag = '' if out == SO else '_' + os.path.basename(out).replace('.so', '')
     nvcc = _nvcc()
     env = dict(os.environ)
     if os.path.exists('/usr/bin/g++'):
@@ -45,20 +48,22 @@ def build(force=False, verbose=False):
     procs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(HERE, 'build', src.replace('.cu', tag + '.o'))
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [nvcc] + ccbin + ['-shared', '-o', SO] + objs + ['-lcudart']
+    cmd = [nvcc] + ccbin + ['-shared', '-o', out] + objs + ['-lcudart']
     subprocess.check_call(cmd, env=env)
-    return SO
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None))

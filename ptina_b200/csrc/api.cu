@@ -13,14 +13,15 @@ void ptb_set_error(const char* fmt, ...) {
 
 TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
-    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
+    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.list = c->d_list; S.nlist = c->list_n; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
     for (int k = 0; k < 3; k++) { S.root_lo[k] = c->root_lo[k]; S.root_hi[k] = c->root_hi[k]; }
     return S;
 }
 int ptb_effective_policy(const ptb_ctx* c, int requested) {
     if (requested == PTB_TRAVERSE_REFERENCE) return PTB_TRAVERSE_REFERENCE;
     bool ok = c->tree_info.valid && c->tree_info.depth <= PTB_STACK;
-    if (!ok) return PTB_TRAVERSE_REFERENCE;                       // AUTO and both ORDERED policies need a proper tree
+    if (!ok) return PTB_TRAVERSE_REFERENCE;
+    if (c->list_overflow && requested != PTB_TRAVERSE_ORDERED_EXACT) return PTB_TRAVERSE_ORDERED_EXACT;   // too many ill-conditioned triangles for the always-test list                       // AUTO and both ORDERED policies need a proper tree
     return requested == PTB_TRAVERSE_ORDERED_EXACT ? PTB_TRAVERSE_ORDERED_EXACT : PTB_TRAVERSE_ORDERED;
 }
 
@@ -111,7 +112,7 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
         dmalloc(&c->d_mc, nf) || dmalloc(&c->d_id, nf) || dmalloc(&c->d_mc_tmp, nf) || dmalloc(&c->d_id_tmp, nf) || dmalloc(&c->d_leaf, nf) ||
         dmalloc(&c->d_child, nf) || dmalloc(&c->d_bmin, nf * 3) || dmalloc(&c->d_bmax, nf * 3) || dmalloc(&c->d_ready, nf) ||
         dmalloc(&c->d_parentcnt, nf * 2) || dmalloc(&c->d_range, nf) || dmalloc(&c->d_height, nf) || dmalloc(&c->d_nodes, nf) ||
-        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_slot_of, nf) || dmalloc(&c->d_gate, nf) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
+        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_slot_of, nf) || dmalloc(&c->d_gate, nf) || dmalloc(&c->d_gbox, 2 * nf) || dmalloc(&c->d_tlo, nf) || dmalloc(&c->d_thi, nf) || dmalloc(&c->d_nlo, nf) || dmalloc(&c->d_nhi, nf) || dmalloc(&c->d_list, PTB_LIST_CAP) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
         delete c; return 1;
     }
     PTB_CUDA(cudaMemset(c->d_film, 0, sizeof(float4) * (size_t)d.max_filmsize * d.max_filmpasses));
@@ -134,8 +135,8 @@ int ptb_destroy(ptb_ctx* c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
-                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_sort_tmp, c->d_scalars,
-                    c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->d_specialq,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
+                    c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->d_pre, c->d_specialq,
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }

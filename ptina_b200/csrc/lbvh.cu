@@ -28,11 +28,12 @@ __device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int f
     return (face_vertex(verts, face, 0) + face_vertex(verts, face, 1) + face_vertex(verts, face, 2)) / 3.0f;
 }
 
-// scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height
+// scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height,
+// [11] always-test list length, [12] list overflow
 __global__ void k_init_scalars(float* s) {
     s[0] = s[1] = s[2] = PTB_INF;
     s[3] = s[4] = s[5] = -PTB_INF;
-    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0;
+    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0;
 }
 
 // lbvh.py:172-176: bounds of the triangle CENTRES (atomic min/max; exact, order-free)
@@ -205,23 +206,127 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
     if (parentcnt[i] != want) scal[9] = 1;
 }
 
-// packed 64-byte node: both children's boxes (leaf child: the triangle's bounds)
-__global__ void __launch_bounds__(BLK) k_pack_nodes(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child,
-                                                    const float* __restrict__ bmin, const float* __restrict__ bmax, int n, Node64* nodes, int* __restrict__ gate) {
+// ---- traversal tree (ptb_traverse.cuh "traversal structure") ------------------------------------------------------------------------
+// Per leaf slot: the triangle's bounds inflated by eps_T, the distance within which Face.intersect's f32 arithmetic can accept a
+// point outside the triangle (derivation in DESIGN.md "Leaf boxes"):
+//   eps_T = 256u * cond * (|u| + |v|) + 64u * (|v0|_inf + |u| + |v|),  cond = uu*vv / |D| = 1 / sin^2(angle(u, v)),  u = 2^-24
+// valid while cond * (36 + 20 * max(|u|/|v|, |v|/|u|)) <= 1e6.  Flags (w of tlo): 1 = NEVER (D == 0 or not finite: s, t are
+// inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> always-test list), 4 = BIG (bounds cover more
+// than 1/16 of the scene's box area: hurts every ancestor's box -> always-test list if there is room).
+#define PTB_TF_NEVER 1
+#define PTB_TF_MUST 2
+#define PTB_TF_BIG 4
+#define PTB_TF_LISTED 8
+__global__ void __launch_bounds__(BLK) k_tri_prep(const float* __restrict__ verts, const int* __restrict__ leaf, int n, const float* __restrict__ scal,
+                                                  float4* __restrict__ tlo, float4* __restrict__ thi) {
+    int s = blockIdx.x * BLK + threadIdx.x;
+    if (s >= n) return;
+    int f = leaf[s];
+    V3 v0 = face_vertex(verts, f, 0), v1 = face_vertex(verts, f, 1), v2 = face_vertex(verts, f, 2);
+    V3 u = v1 - v0, v = v2 - v0;
+    float uu = dot(u, u), uv = dot(u, v), vv = dot(v, v);
+    float D = uv * uv - uu * vv;
+    V3 lo = vmin(vmin(v0, v1), v2), hi = vmax(vmax(v0, v1), v2);
+    int flags = 0;
+    float eps = 0.0f;
+    if (!(fabsf(D) > 0.0f) || !(fabsf(D) <= 3e38f)) flags = PTB_TF_NEVER;
+    else {
+        float lu = sqrtf(uu), lv = sqrtf(vv);
+        float cond = uu * vv / fabsf(D);
+        float q = fmaxf(lu, lv) / fminf(lu, lv);
+        if (!(cond * (36.0f + 20.0f * q) <= 1e6f)) flags = PTB_TF_MUST;
+        else {
+            const float U = 5.9604644775390625e-8f;
+            float vmaxabs = fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fabsf(v0.z));
+            eps = 1.01f * (256.0f * U * cond * (lu + lv) + 64.0f * U * (vmaxabs + lu + lv));
+            if (!(eps <= 3e38f)) flags = PTB_TF_MUST;
+        }
+        // scene extent = extent of the triangle centres (lbvh.py:172-176), the only bounds known before the boxes are built
+        V3 e = mk3(scal[3] - scal[0], scal[4] - scal[1], scal[5] - scal[2]), d = hi - lo;
+        float scene = e.x * e.y + e.y * e.z + e.z * e.x, own = d.x * d.y + d.y * d.z + d.z * d.x;
+        if (own > scene * (1.0f / 16.0f)) flags |= PTB_TF_BIG;
+    }
+    tlo[s] = make_float4(__fadd_rd(lo.x, -eps), __fadd_rd(lo.y, -eps), __fadd_rd(lo.z, -eps), __int_as_float(flags));
+    thi[s] = make_float4(__fadd_ru(hi.x, eps), __fadd_ru(hi.y, eps), __fadd_ru(hi.z, eps), 0.0f);
+}
+// always-test list, in slot order (one block): every MUST slot, then BIG slots while there is room.  scal[11] = entries,
+// scal[12] = 1 if the MUST slots alone overflow the list (the production traversal is then not used).
+__global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, int n, int cap, int* __restrict__ list, int* scal) {
+    __shared__ int s_count, s_warp[32];
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+        const int want = pass == 0 ? PTB_TF_MUST : PTB_TF_BIG;
+        for (int base = 0; base < n; base += 1024) {
+            int s = base + threadIdx.x;
+            int fl = s < n ? __float_as_int(tlo[s].w) : 0;
+            bool take = (fl & want) != 0 && (fl & (PTB_TF_NEVER | PTB_TF_LISTED)) == 0;
+            unsigned m = __ballot_sync(0xffffffffu, take);
+            int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            if (lane == 0) s_warp[w] = __popc(m);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int k = 0; k < 32; k++) { int c = s_warp[k]; if (k < w) before += c; total += c; }
+            int pos = s_count + before + __popc(m & ((1u << lane) - 1u));
+            if (take && pos < cap) { list[pos] = s; float4 t = tlo[s]; t.w = __int_as_float(fl | PTB_TF_LISTED); tlo[s] = t; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (pass == 0 && s_count + total > cap) scal[12] = 1;
+                s_count = min(cap, s_count + total);
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) scal[11] = s_count;
+}
+// traversal boxes, level by level (`ready` holds the sweep in which the reference box of a node was completed, so the children
+// of a node of level `stamp` belong to earlier levels): union of the inflated bounds of the unlisted leaves below the node.
+// Empty = (lo, hi) = (+1e30, -1e30).
+__global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ child, const int* __restrict__ ready, int n, int stamp,
+                                                    const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* __restrict__ nlo, float4* __restrict__ nhi) {
     int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= n - 1) return;
+    if (i >= n - 1 || ready[i] != stamp) return;
     int2 ch = child[i];
-    V3 lo[2], hi[2];
+    V3 lo = v3s(1e30f), hi = v3s(-1e30f);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         int c = k == 0 ? ch.x : ch.y;
-        if (c < 0 || c >= 2 * n - 1) { lo[k] = v3s(0.0f); hi[k] = v3s(0.0f); }
-        else if (c < n) { face_box(verts, leaf[c], &lo[k], &hi[k]); gate[c] = i; }
-        else { int j = c - n; lo[k] = mk3(bmin[3 * j], bmin[3 * j + 1], bmin[3 * j + 2]); hi[k] = mk3(bmax[3 * j], bmax[3 * j + 1], bmax[3 * j + 2]); }
+        float4 a, b;
+        if (c < n) { a = tlo[c]; b = thi[c]; if (__float_as_int(a.w) & (PTB_TF_NEVER | PTB_TF_LISTED)) continue; }
+        else { a = nlo[c - n]; b = nhi[c - n]; }
+        lo = vmin(lo, mk3(a.x, a.y, a.z)); hi = vmax(hi, mk3(b.x, b.y, b.z));
+    }
+    nlo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f); nhi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+// packed 64-byte traversal node: both children's traversal boxes and ids (-1 = nothing below: listed / never-hit leaf or an
+// internal node with an empty box); per leaf slot: its gate (parent) and the gate's REFERENCE box (bmin/bmax of the parent).
+__global__ void __launch_bounds__(BLK) k_pack_nodes(const int2* __restrict__ child, const float* __restrict__ bmin, const float* __restrict__ bmax, int n,
+                                                    const float4* __restrict__ tlo, const float4* __restrict__ thi, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                                                    Node64* nodes, int* __restrict__ gate, float4* __restrict__ gbox) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    int2 ch = child[i];
+    float4 lo[2], hi[2]; int id[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int c = k == 0 ? ch.x : ch.y;
+        id[k] = c;
+        lo[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); hi[k] = lo[k];
+        if (c < 0 || c >= 2 * n - 1) id[k] = -1;
+        else if (c < n) {
+            lo[k] = tlo[c]; hi[k] = thi[c];
+            if (__float_as_int(lo[k].w) & (PTB_TF_NEVER | PTB_TF_LISTED)) id[k] = -1;
+            gate[c] = i;
+            gbox[2 * c] = make_float4(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2], 0.0f);
+            gbox[2 * c + 1] = make_float4(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2], 0.0f);
+        } else {
+            lo[k] = nlo[c - n]; hi[k] = nhi[c - n];
+            if (lo[k].x > hi[k].x) id[k] = -1;
+        }
     }
     Node64 N;
-    N.a = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ch.x));
-    N.b = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(ch.y));
+    N.a = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(id[0]));
+    N.b = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(id[1]));
     N.c = make_float4(lo[1].x, lo[1].y, lo[1].z, 0.0f);
     N.d = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.0f);
     nodes[i] = N;
@@ -307,8 +412,12 @@ int ptb_lbvh_build(ptb_ctx* c) {
             return 2;
         }
         k_validate<<<nblk(2 * n - 1), BLK, 0, st>>>(c->d_parentcnt, n, c->d_scalars);
-        k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, c->d_bmin, c->d_bmax, n, c->d_nodes, c->d_gate);
-        c->launches += 2;
+        // traversal structure: inflated leaf bounds, always-test list, pruned traversal boxes, packed nodes
+        k_tri_prep<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, scal, c->d_tlo, c->d_thi);
+        k_build_list<<<1, 1024, 0, st>>>(c->d_tlo, n, PTB_LIST_CAP, c->d_list, c->d_scalars);
+        for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
+        k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_bmin, c->d_bmax, n, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_nodes, c->d_gate, c->d_gbox);
+        c->launches += 4 + sweeps;
     }
     if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }
     PTB_CUDA(cudaEventRecord(e1, st));
@@ -323,6 +432,8 @@ int ptb_lbvh_build(ptb_ctx* c) {
         PTB_CUDA(cudaStreamSynchronize(st));
         valid = (n > 1) && h_scal[9] == 0;
         depth = valid ? h_scal[10] : 0;
+        c->list_n = n > 1 ? h_scal[11] : 0;
+        c->list_overflow = n > 1 ? h_scal[12] : 0;
         for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
     }
     PTB_CUDA(cudaGetLastError());

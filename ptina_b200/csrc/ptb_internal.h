@@ -9,6 +9,7 @@
 #include "ptb_traverse.cuh"
 
 #define PTB_SOBOL_ROWS 21
+#define PTB_LIST_CAP 32
 
 void ptb_set_error(const char* fmt, ...);
 #define PTB_CUDA(call)                                                                        \
@@ -89,6 +90,11 @@ struct ptb_ctx {
     Tri64* d_tris = nullptr;
     int32_t* d_slot_of = nullptr;   // face id -> leaf slot
     int32_t* d_gate = nullptr;      // leaf slot -> parent internal node (the box that gates its triangle test)
+    float4* d_gbox = nullptr;       // [2n] per leaf slot: the reference box (lo, hi) of its gate
+    float4 *d_tlo = nullptr, *d_thi = nullptr;   // [n] per leaf slot: inflated triangle bounds (w of tlo: PTB_TF_* flags)
+    float4 *d_nlo = nullptr, *d_nhi = nullptr;   // [n-1] per internal node: traversal box (union of the unlisted leaves below)
+    int32_t* d_list = nullptr;      // always-test list (leaf slots), PTB_LIST_CAP entries
+    int list_n = 0, list_overflow = 0;
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)
     ptb_tree_info tree_info{};
@@ -104,6 +110,7 @@ struct ptb_ctx {
     PathState st{};
     RayQueue xq[2]{};               // extend queues (in / out, swapped every bounce)
     RayQueue sq{};                  // shadow queue
+    float4* d_pre = nullptr;        // provisional closest hit over the always-test list, per extend-queue position
     int* d_specialq = nullptr;      // queue positions of rays the conservative kernel set aside
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;

@@ -23,32 +23,45 @@
 #define PTB_FETCH_MIN 6             /* idle lanes that trigger a refill from the staged tile */
 #endif
 
-struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; };
+struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; float4 pre; bool dead; };
 
-// ---- extend queue: closest hit for path p (path.py:28-29).  Records: q0 = (origin, path), q1 = (unit direction, avoid slot) -------
+// Record formats (float4 arrays indexed by queue position):
+//   q0 = (origin, path slot)                                                               -- every queue
+//   q1 = (unit direction, avoid leaf slot)                 extend   |  (direction, distance to the light sample)   shadow
+//   q2 = provisional closest hit over the always-test list  extend  |  (contribution if unoccluded, avoid leaf slot) shadow
+//        (depth, u, v, leaf slot or -1; written by k_trace_list, present iff PRE)
+// A shadow record whose distance is negative is dead: k_trace_list found an occluder in the always-test list.
+
+// ---- extend queue: closest hit for path p (path.py:28-29) ---------------------------------------------------------------------------
+template <bool PRE>
 struct ExtendIO {
     static constexpr bool kAnyHit = false;
-    static constexpr int K = 2;
-    const float4* __restrict__ q0; const float4* __restrict__ q1; float4* hit;
-    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : q1; }
-    PTB_D void decode(const float4* r, RayIn* in) const {
-        in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
-        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->avoid_slot = __float_as_int(r[1].w); in->tmax = PTB_INF;
-    }
-    PTB_D void store(int p, const HitRec& h, V3) const { hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1)); }
-};
-// ---- shadow queue: Ray(hitpos, li.dir) against avoid = hit triangle; unoccluded -> add the pending contribution (path.py:49-55).
-// Records: q0 = (origin, path), q1 = (direction as sampled -- not re-normalised, like the reference --, distance), q2 = (contribution,
-// avoid slot).  Exactly one shadow ray per path per launch touches result[p], so the reduction `red.add` computes the same single
-// rounded sum as a load-add-store, without making the warp wait for the load.
-struct ShadowIO {
-    static constexpr bool kAnyHit = true;
-    static constexpr int K = 3;
-    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2; float4* result;
+    static constexpr bool kPre = PRE;
+    static constexpr int K = PRE ? 3 : 2;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; float4* q2; float4* hit;
     PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
     PTB_D void decode(const float4* r, RayIn* in) const {
         in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
-        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->tmax = r[1].w;
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->avoid_slot = __float_as_int(r[1].w); in->tmax = PTB_INF;
+        if (PRE) in->pre = r[K - 1];
+    }
+    PTB_D void store(int p, const HitRec& h, V3) const { hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1)); }
+    PTB_D void store_pre(int idx, const HitRec& h, bool) const { q2[idx] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.slot : -1)); }
+    PTB_D void store_dead(int) const {}
+};
+// ---- shadow queue: Ray(hitpos, li.dir) against avoid = hit triangle; unoccluded -> add the pending contribution (path.py:49-55).
+// The direction is used as sampled (not re-normalised, like the reference).  Exactly one shadow ray per path per launch touches
+// result[p], so the reduction `red.add` computes the same single rounded sum as a load-add-store, without making the warp wait
+// for the load.
+struct ShadowIO {
+    static constexpr bool kAnyHit = true;
+    static constexpr bool kPre = false;
+    static constexpr int K = 3;
+    const float4* __restrict__ q0; float4* q1; const float4* __restrict__ q2; float4* result;
+    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
+    PTB_D void decode(const float4* r, RayIn* in) const {
+        in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->tmax = r[1].w; in->dead = r[1].w < 0.0f;
         in->c = mk3(r[2].x, r[2].y, r[2].z); in->avoid_slot = __float_as_int(r[2].w);
     }
     PTB_D void store(int p, const HitRec& h, V3 c) const {
@@ -56,25 +69,33 @@ struct ShadowIO {
         float* r = reinterpret_cast<float*>(&result[p]);
         atomicAdd(r, c.x); atomicAdd(r + 1, c.y); atomicAdd(r + 2, c.z);
     }
+    PTB_D void store_pre(int idx, const HitRec&, bool occluded) const { if (occluded) q1[idx].w = -1.0f; }
+    PTB_D void store_dead(int) const {}
 };
 // ---- parity taps: the same record formats (written by k_pack_tap), results into flat arrays -------------------------------------------
-template <bool ANYHIT>
+template <bool ANYHIT, bool PRE>
 struct TapIO {
     static constexpr bool kAnyHit = ANYHIT;
-    static constexpr int K = ANYHIT ? 3 : 2;
-    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2;
+    static constexpr bool kPre = PRE && !ANYHIT;
+    static constexpr int K = (ANYHIT || PRE) ? 3 : 2;
+    const float4* __restrict__ q0; float4* q1; float4* q2;
     int* hit; float* depth; int* index; float* uv;
     PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
     PTB_D void decode(const float4* r, RayIn* in) const {
         in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
         in->rd = mk3(r[1].x, r[1].y, r[1].z);
-        if (ANYHIT) { in->tmax = r[1].w; in->avoid_slot = __float_as_int(r[2].w); }
-        else { in->tmax = PTB_INF; in->avoid_slot = __float_as_int(r[1].w); }
+        if (ANYHIT) { in->tmax = r[1].w; in->dead = r[1].w < 0.0f; in->avoid_slot = __float_as_int(r[K - 1].w); }
+        else { in->tmax = PTB_INF; in->avoid_slot = __float_as_int(r[1].w); if (PRE) in->pre = r[K - 1]; }
     }
     PTB_D void store(int i, const HitRec& h, V3) const {
         hit[i] = h.hit;
         if (!ANYHIT) { depth[i] = h.depth; index[i] = h.index; uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
     }
+    PTB_D void store_pre(int idx, const HitRec& h, bool occluded) const {
+        if (ANYHIT) { if (occluded) q1[idx].w = -1.0f; }
+        else q2[idx] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.slot : -1));
+    }
+    PTB_D void store_dead(int i) const { hit[i] = 1; }
 };
 // ---- rays the production kernel set aside (axis-parallel / non-finite): queue positions listed in `list` -----------------------
 template <class IO>
@@ -100,7 +121,7 @@ PTB_D void fetch_direct(const IO& io_any, int i, RayIn* in) {
     float4 r[IO::K];
 #pragma unroll
     for (int k = 0; k < IO::K; k++) r[k] = io.rec(k)[pos];
-    in->c = v3s(0.0f);
+    in->c = v3s(0.0f); in->dead = false; in->pre = make_float4(PTB_INF, 0.0f, 0.0f, __int_as_float(-1));
     io.decode(r, in);
 }
 
@@ -137,7 +158,8 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO
             fetch_direct(io, idx, &in);
             const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
             HitRec h;
-            if (POLICY == 0) {
+            if (in.dead) { h.hit = 1; h.depth = 0.0f; h.index = -1; h.u = h.v = 0.0f; h.slot = -1; }     // occluded by the always-test list
+            else if (POLICY == 0) {
                 h = trace_reference<COUNT>(S, in.ro, in.rd, avoid, &C);
                 if (IO::kAnyHit) h.hit = !(h.hit == 0 || h.depth > in.tmax);       // path.py:50  occ.hit == 0 or occ.depth > li.dis
             } else {
@@ -150,6 +172,51 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO
     flush_counters<COUNT>(C, nrays, IO::kAnyHit, ctr);
 }
 
+// ---- always-test list pre-pass: one ray per thread, every thread of a warp tests the same triangle (broadcast loads, no
+// divergence in the loop).  Extend: writes the provisional closest hit over the list (q2).  Shadow: marks occluded rays dead.
+// Axis-parallel / non-finite rays are left untouched (k_trace sets them aside for k_trace_simple<1>, which tests every triangle).
+template <class IO, bool COUNT>
+__global__ void __launch_bounds__(256) k_trace_list(TraceScene S, IO io, const int* count_ptr, DevCounters* ctr) {
+    constexpr bool ANYHIT = IO::kAnyHit;
+    const int count = *count_ptr;
+    unsigned long long ntris = 0;
+    for (int idx = blockIdx.x * 256 + threadIdx.x; idx < count; idx += gridDim.x * 256) {
+        RayIn in;
+        fetch_direct(io, idx, &in);
+        HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
+        bool occluded = false;
+        if (!ray_is_special(in.ro, in.rd)) {
+            const RayCons R = ray_cons(in.ro, in.rd);
+            float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
+            for (int j = 0; j < S.nlist; j++) {
+                const int slot = S.list[j];
+                if (slot == in.avoid_slot) continue;
+                const Tri64 T = S.tris[slot];
+                if (COUNT) ntris++;
+                float dep, s, t;
+                if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
+                    const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+                    if (better) {
+                        // the reference tests this triangle only if its gate passes Box.intersect: conservative, exact when grazing
+                        const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
+                        float gl; bool gsure;
+                        if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], in.ro, in.rd))) {
+                            ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep;
+                            if (ANYHIT) { occluded = true; break; }
+                        }
+                    }
+                }
+            }
+        }
+        IOTraits<IO>::base(io).store_pre(idx, ret, occluded);
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ntris += __shfl_xor_sync(0xffffffffu, ntris, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->tris, ntris);
+    }
+}
+
 // ---- cp.async helpers (16-byte global -> shared copies, per-thread groups) --------------------------------------------------------------
 PTB_D void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -159,6 +226,9 @@ PTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memo
 template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 #define PTB_PQ 4                    /* pending-leaf ring entries per lane */
+#ifndef PTB_NODE_REPS
+#define PTB_NODE_REPS 1             /* node steps per vote */
+#endif
 #define PTB_TRACE_BLK_S 768         /* threads of the shared-memory-resident variant (one CTA per SM) */
 
 // dynamic shared memory layout of k_trace (bytes), shared by the kernel and the host launch code
@@ -227,17 +297,16 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
     // ---- per-lane ray state ----
     int item = -1, avoid_slot = -1;            // item >= 0: this lane owns a ray (its result is stored when the lane next goes idle)
     RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
+    float kL = 0.0f, aL = 0.0f;                // margins of the traversal-tree boxes (leaf_margins)
     V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-    // stack entries: low word = internal node | SURE_BIT (its own box certainly passes the reference's test), high word = lower
-    // bound of its entry distance.  The top lives in `tos` (valid iff sp > 0; reloaded at pop time, consumed at the next pop), the
-    // entries below it in stack[1 .. sp-1].
-    constexpr unsigned SURE_BIT = 0x80000000u;
+    // stack entries: low word = internal node, high word = lower bound of the depth of anything below it.  The top lives in `tos`
+    // (valid iff sp > 0; reloaded at pop time, consumed at the next pop), the entries below it in stack[1 .. sp-1].
     unsigned long long stack[PTB_STACK + 1];
     unsigned long long tos = 0;
     int sp = 0;
-    int cur = -1;                              // node to visit next (| SURE_BIT), -1: take it from the stack
+    int cur = -1;                              // node to visit next, -1: take it from the stack
     float cur_near = 0.0f;
     int q_head = 0, q_count = 0;
 
@@ -260,19 +329,27 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
                 float4 r[K];
 #pragma unroll
                 for (int j = 0; j < K; j++) r[j] = s_tile[warp][cur_buf][j][k];
-                RayIn in; in.c = v3s(0.0f);
+                RayIn in; in.c = v3s(0.0f); in.dead = false;
                 io.decode(r, &in);
                 if (ray_is_special(in.ro, in.rd)) {
                     special_list[atomicAdd(special_count, 1)] = (cur_buf == 0 ? tile_base0 : tile_base1) + k;    // traced by k_trace_simple<1> afterwards (rare)
+                } else if (in.dead) {                                      // occluded by the always-test list: nothing to trace
+                    io.store_dead(in.item);
                 } else {
                     if (COUNT) nrays++;
                     item = in.item; avoid_slot = in.avoid_slot; contrib = in.c;
                     R = ray_cons(in.ro, in.rd);
-                    best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
-                    cull = best + best * PTB_CULL_GUARD;
+                    leaf_margins(R, &kL, &aL);
                     ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
+                    if (IO::kPre) {                                         // provisional closest hit over the always-test list
+                        ret.slot = __float_as_int(in.pre.w); ret.hit = ret.slot >= 0;
+                        ret.depth = in.pre.x; ret.u = in.pre.y; ret.v = in.pre.z;
+                        if (ret.hit) ret.index = S.leaf[ret.slot];
+                    }
+                    best = ANYHIT ? fminf(in.tmax, PTB_INF) : ret.depth;
+                    cull = best + best * PTB_CULL_GUARD;
                     sp = 0; cur_near = 0.0f; q_head = 0; q_count = 0;
-                    cur = 0;            // the root: its own box is implied by its descendants' boxes (monotone slab test); not `sure`
+                    cur = 0;            // the root (its children's boxes are tested in its node step)
                 }
             }
             tile_pos = min(tile_pos + __popc(idle), nv);
@@ -285,69 +362,67 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
         }
         if ((mn | ml) == 0u) break;                    // exhausted and nothing in flight
         if (__popc(mn) > __popc(ml)) {
-            // ---- node step: one 64-byte node, both children's conservative slab tests ---------------------------------------------------------
-            if (node_ok) {
+            // ---- node step: one 64-byte node, both children's slab tests ----------------------------------------------------------------------
+#pragma unroll 1
+            for (int rep = 0; rep < PTB_NODE_REPS; rep++)
+            if (rep == 0 ? node_ok : ((cur != -1 || sp > 0) && q_count <= PTB_PQ - 2)) {
                 if (cur == -1) {                        // pop (the reload of `tos` is not consumed before the next pop)
                     cur = (int)(unsigned)tos; cur_near = __int_as_float((int)(tos >> 32));
                     --sp;
                     tos = stack[sp];
                 }
-                if (cur_near > cull) cur = -1;          // entered beyond the best hit found since it was pushed / chosen
+                if (cur_near > cull) cur = -1;          // nothing below can beat the best hit found since it was pushed / chosen
                 else {
-                    const bool cur_sure = ((unsigned)cur & SURE_BIT) != 0u;
-                    const int ci = (int)((unsigned)cur & ~SURE_BIT);
                     Node64 N;
-                    if (SMEM) { N.a = s_node[ci]; N.b = s_node[(n - 1) + ci]; N.c = s_node[2 * (n - 1) + ci]; N.d = s_node[3 * (n - 1) + ci]; }
-                    else N = S.nodes[ci];
+                    if (SMEM) { N.a = s_node[cur]; N.b = s_node[(n - 1) + cur]; N.c = s_node[2 * (n - 1) + cur]; N.d = s_node[3 * (n - 1) + cur]; }
+                    else N = S.nodes[cur];
                     if (COUNT) { C.nodes++; C.boxes += 2; }
-                    const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
-                    float n0, n1; bool s0, s1;
-                    const bool h0 = slab_cons2(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, R, &n0, &s0);
-                    const bool h1 = slab_cons2(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, R, &n1, &s1);
+                    const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);      // -1: nothing below
+                    float n0, n1;
+                    const bool h0 = slab_trav(N.a, N.b, R, kL, aL, &n0) && !(n0 > cull) && c0 >= 0;
+                    const bool h1 = slab_trav(N.c, N.d, R, kL, aL, &n1) && !(n1 > cull) && c1 >= 0;
                     const bool leaf0 = c0 < n, leaf1 = c1 < n;
-                    const bool in0 = !(n0 > cull), in1 = !(n1 > cull);
-                    // a leaf is a candidate whenever its parent (this node) was reached; its own bounds only allow the distance cull.
-                    // It inherits this node's `sure` flag: this node's box is its gate.
-                    const bool p0 = leaf0 && c0 != avoid_slot && (in0 || !h0);
-                    const bool p1 = leaf1 && c1 != avoid_slot && (in1 || !h1);
-                    const unsigned sure_bit = cur_sure ? SURE_BIT : 0u;
-                    if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = (int)((unsigned)c0 | sure_bit); s_qnear[k][threadIdx.x] = h0 ? n0 : 0.0f; q_count++; }
-                    if (p1) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = (int)((unsigned)c1 | sure_bit); s_qnear[k][threadIdx.x] = h1 ? n1 : 0.0f; q_count++; }
-                    const bool d0 = !leaf0 && h0 && in0, d1 = !leaf1 && h1 && in1;
-                    const int e0 = (int)((unsigned)(c0 - n) | (s0 ? SURE_BIT : 0u)), e1 = (int)((unsigned)(c1 - n) | (s1 ? SURE_BIT : 0u));
+                    const bool p0 = h0 && leaf0 && c0 != avoid_slot, p1 = h1 && leaf1 && c1 != avoid_slot;
+                    if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c0; s_qnear[k][threadIdx.x] = n0; q_count++; }
+                    if (p1) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c1; s_qnear[k][threadIdx.x] = n1; q_count++; }
+                    const bool d0 = h0 && !leaf0, d1 = h1 && !leaf1;
                     const bool first1 = !(n0 < n1);     // nearer first
                     if (d0 && d1) {
                         stack[sp] = tos;                // slot 0 receives garbage when sp == 0 (never read back as an entry)
-                        tos = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)(first1 ? e0 : e1);
+                        tos = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
                         sp++;                           // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
                         if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
-                        cur = first1 ? e1 : e0; cur_near = first1 ? n1 : n0;
-                    } else if (d0) { cur = e0; cur_near = n0; }
-                    else if (d1) { cur = e1; cur_near = n1; }
+                        cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
+                    } else if (d0) { cur = c0 - n; cur_near = n0; }
+                    else if (d1) { cur = c1 - n; cur_near = n1; }
                     else cur = -1;
                 }
             }
         } else {
-            // ---- leaf step: the oldest pending triangle of every lane that has one -----------------------------------------------------------
+            // ---- leaf step: the oldest pending leaf of every lane that has one ---------------------------------------------------------------
             if (leaf_ok) {
-                const unsigned qs = (unsigned)s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
+                const int slot = s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
                 q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
-                const int slot = (int)(qs & ~SURE_BIT);
                 if (!(lnear > cull)) {
-                    Tri64 T;
-                    if (SMEM) { T.a = s_tri[slot]; T.b = s_tri[n + slot]; T.c = s_tri[2 * n + slot]; T.d = s_tri[3 * n + slot]; }
-                    else T = S.tris[slot];
-                    if (COUNT) C.tris++;
-                    float dep, s, t;
-                    if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
-                        // here dep <= best; the candidate counts only if the reference reaches it: its gate passes the exact slab test
-                        // (known from the conservative bounds unless the ray grazes the gate)
-                        const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
-                        if (better && ((qs & SURE_BIT) != 0u || gate_passes(S, S.gate[slot], R.o, R.d))) {
-                            ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
-                            ret.index = S.leaf[slot];                         // face id: only read when the ray is stored
-                            if (ANYHIT) { cur = -1; sp = 0; q_count = 0; }    // occluded: done with this ray (stored when the lane is refilled)
-                            else { best = dep; cull = dep + dep * PTB_CULL_GUARD; }
+                    // the reference tests this triangle only if its gate box passes Box.intersect: conservative test first
+                    float4 glo, ghi;
+                    glo = S.gbox[2 * slot]; ghi = S.gbox[2 * slot + 1];
+                    float gl; bool gsure;
+                    if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure)) {
+                        Tri64 T;
+                        if (SMEM) { T.a = s_tri[slot]; T.b = s_tri[n + slot]; T.c = s_tri[2 * n + slot]; T.d = s_tri[3 * n + slot]; }
+                        else T = S.tris[slot];
+                        if (COUNT) C.tris++;
+                        float dep, s, t;
+                        if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
+                            // here dep <= best.  `gsure`: the gate certainly passes; otherwise the ray grazes it: exact test
+                            const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+                            if (better && (gsure || gate_passes(S, S.gate[slot], R.o, R.d))) {
+                                ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
+                                ret.index = S.leaf[slot];                         // face id: only read when the ray is stored
+                                if (ANYHIT) { cur = -1; sp = 0; q_count = 0; }    // occluded: done (stored when the lane is refilled)
+                                else { best = dep; cull = dep + dep * PTB_CULL_GUARD; }
+                            }
                         }
                     }
                 }

@@ -32,6 +32,9 @@ struct TraceScene {
     const int* __restrict__ leaf;        // [n]  slot -> face id      (lbvh.py:55)
     const int* __restrict__ slot_of;     // [n]  face id -> slot      (inverse of leaf, proper trees only)
     const int* __restrict__ gate;        // [n]  slot -> internal node whose child the leaf is (its box gates the triangle test)
+    const float4* __restrict__ gbox;     // [2n] slot -> reference box (lo, hi) of its gate
+    const int* __restrict__ list;        // always-test list (leaf slots): big or ill-conditioned triangles kept out of the traversal tree
+    int nlist;
     // reference arrays (lbvh.py:50-59) for the literal traversal
     const float* __restrict__ bmin;      // [n-1][3]
     const float* __restrict__ bmax;      // [n-1][3]
@@ -175,6 +178,38 @@ PTB_D bool slab_cons2(float lox, float loy, float loz, float hix, float hiy, flo
     return !(l > ub);
 }
 
+// ---- traversal structure (production kernel) -------------------------------------------------------------------------------------
+// With the gate lemma above, the reference's answer is: the smallest f32 depth (ties: largest leaf slot) over the triangles T that
+// (i) pass Face.intersect in f32 and (ii) whose gate passes Box.intersect in f32.  Any structure that enumerates a superset of the
+// triangles satisfying (i) gives the same answer once (ii) is checked per candidate.  The traversal tree keeps the LBVH topology
+// but bounds every node by the union of the INFLATED bounds of the triangles below it -- inflated by eps_T, the distance within
+// which the f32 arithmetic of Face.intersect can accept a point outside the triangle (lbvh.cu k_tri_prep) -- and leaves
+// out triangles that would spoil it: big ones (their bounds make every ancestor's box huge) and ill-conditioned ones (no usable
+// eps_T) go to a short always-test list.  The ray-side part of the bound: if T is accepted at depth r then the real point
+// ro + r*rd lies within eps_T + 64u(|ro|_1 + r|rd|_1) of T's bounds, i.e. r lies in the slab interval of the inflated box widened by
+// 64u(|ro|_1 + r|rd|_1) * max|1/d|.  leaf_margins() turns that (plus the rounding of the 1-FMA slab arithmetic) into the relative /
+// absolute margins (kL, aL) used for every box of the traversal tree.
+PTB_D void leaf_margins(const RayCons& R, float* kL, float* aL) {
+    const float U = 5.9604644775390625e-8f;
+    const float rmax = fmaxf(fmaxf(fabsf(R.r.x), fabsf(R.r.y)), fabsf(R.r.z));
+    const float d1 = fabsf(R.d.x) + fabsf(R.d.y) + fabsf(R.d.z), o1 = fabsf(R.o.x) + fabsf(R.o.y) + fabsf(R.o.z);
+    *kL = 8.0f * U + 160.0f * U * d1 * rmax;
+    *aL = R.a2 + 160.0f * U * o1 * rmax;
+}
+// slab test of a traversal-tree box with margins (k, a): false only if no triangle below can be accepted; *lb <= depth of
+// anything accepted below.
+PTB_D bool slab_trav(float4 lo, float4 hi, const RayCons& R, float k, float a, float* lb) {
+    const float x1 = __fmaf_rn(lo.x, R.r.x, R.nc.x), x2 = __fmaf_rn(hi.x, R.r.x, R.nc.x);
+    const float y1 = __fmaf_rn(lo.y, R.r.y, R.nc.y), y2 = __fmaf_rn(hi.y, R.r.y, R.nc.y);
+    const float z1 = __fmaf_rn(lo.z, R.r.z, R.nc.z), z2 = __fmaf_rn(hi.z, R.r.z, R.nc.z);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
+    const float l = __fmaf_rn(-tn, k, tn) - a;
+    const float ub = __fmaf_rn(fabsf(tf), k, tf);
+    *lb = l;
+    return !(l > ub);
+}
+
 // geometries.py:117-148 on the packed record, literal (true divisions).  Returns hit; depth/s/t as the reference.
 PTB_D bool tri_ref(const Tri64& T, V3 ro, V3 rd, float* depth, float* s_out, float* t_out) {
     V3 v0 = mk3(T.a.x, T.a.y, T.a.z), u = mk3(T.b.x, T.b.y, T.b.z), v = mk3(T.c.x, T.c.y, T.c.z), nrm = mk3(T.d.x, T.d.y, T.d.z);
@@ -260,8 +295,10 @@ PTB_D HitRec trace_reference(const TraceScene& S, V3 ro, V3 rd, int avoid, Trace
     return ret;
 }
 
-// ---- ordered traversal over packed nodes ("while-while": all lanes of a warp run node steps together, then the
-// pending leaves together) ---------------------------------------------------------------------------------------
+// ---- ordered traversal with the EXACT predicates, over the reference's own arrays (child / bmin / bmax) ----------------------
+// Near child first; sub-trees whose exact entry distance is beyond the current best (plus a relative guard band: the compare mixes
+// a box distance with a triangle distance, which are rounded differently) are skipped; ties in depth go to the larger leaf slot.
+// The checker for the production kernel (PTB_TRAVERSE_ORDERED_EXACT) and the tracer of the rays it sets aside.
 // ANYHIT: stop at the first accepted triangle with depth <= tmax (shadow rays: the reference calls the ray occluded
 // iff its CLOSEST hit has depth <= dis, which holds iff ANY reachable triangle has one).
 template <bool ANYHIT, bool COUNT>
@@ -273,37 +310,33 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
         return ret;
     }
     const RayPre P = ray_pre(ro, rd);
-    {   // the root's own box (the reference pops and tests it first)
-        float nr;
-        if (COUNT) C->boxes++;
-        if (!slab_fast(S.root_lo[0], S.root_lo[1], S.root_lo[2], S.root_hi[0], S.root_hi[1], S.root_hi[2], P, &nr)) return ret;
-    }
+    float nr;
+    if (COUNT) C->boxes++;
+    // the root's own box (the reference pops and tests it first)
+    if (!slab_fast(S.bmin[0], S.bmin[1], S.bmin[2], S.bmax[0], S.bmax[1], S.bmax[2], P, &nr)) return ret;
     const int avoid_slot = avoid >= 0 ? S.slot_of[avoid] : -1;
-    // a triangle is accepted iff depth < best (ties: larger slot wins, = the leaf the reference visits first); sub-trees
-    // entered beyond `cull` = best * (1 + 2^-12) are skipped
     float best = ANYHIT ? fminf(tmax, PTB_INF) : PTB_INF;
     float cull = best + best * PTB_CULL_GUARD;
     int stack_id[PTB_STACK];
     float stack_near[PTB_STACK];
     int sp = 0;
-    int cur = 0;          // internal node index, -1 = none
+    int cur = 0;          // internal node whose box passed, -1 = none
     float cur_near = 0.0f;
     while (true) {
         int pend0 = -1, pend1 = -1;
         while (cur >= 0) {
             if (cur_near > cull) { cur = -1; break; }
-            const Node64 N = S.nodes[cur];
+            const int2 ch = S.child[cur];
             if (COUNT) C->nodes++;
-            const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);
+            const int c0 = ch.x, c1 = ch.y;
             const bool leaf0 = c0 < n, leaf1 = c1 < n;
             float n0 = 0.0f, n1 = 0.0f;
             bool d0 = false, d1 = false;
-            if (!leaf0) { d0 = slab_fast(N.a.x, N.a.y, N.a.z, N.b.x, N.b.y, N.b.z, P, &n0) && !(n0 > cull); if (COUNT) C->boxes++; }
-            if (!leaf1) { d1 = slab_fast(N.c.x, N.c.y, N.c.z, N.d.x, N.d.y, N.d.z, P, &n1) && !(n1 > cull); if (COUNT) C->boxes++; }
+            if (!leaf0) { const int j = c0 - n; d0 = slab_fast(S.bmin[3 * j], S.bmin[3 * j + 1], S.bmin[3 * j + 2], S.bmax[3 * j], S.bmax[3 * j + 1], S.bmax[3 * j + 2], P, &n0) && !(n0 > cull); if (COUNT) C->boxes++; }
+            if (!leaf1) { const int j = c1 - n; d1 = slab_fast(S.bmin[3 * j], S.bmin[3 * j + 1], S.bmin[3 * j + 2], S.bmax[3 * j], S.bmax[3 * j + 1], S.bmax[3 * j + 2], P, &n1) && !(n1 > cull); if (COUNT) C->boxes++; }
             if (leaf0 && c0 != avoid_slot) pend0 = c0;
             if (leaf1 && c1 != avoid_slot) { if (pend0 < 0) pend0 = c1; else pend1 = c1; }
             if (d0 && d1) {
-                // nearer first; on equal entry distance child1 first, like the reference
                 const bool first1 = !(n0 < n1);
                 if (sp < PTB_STACK) { stack_id[sp] = (first1 ? c0 : c1) - n; stack_near[sp] = first1 ? n0 : n1; sp++; }
                 if (COUNT) C->max_stack = max(C->max_stack, (unsigned)sp);

@@ -146,8 +146,11 @@ PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict_
 }
 
 // ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
+#ifndef PTB_SHADE_MINBLOCKS
+#define PTB_SHADE_MINBLOCKS 1
+#endif
 template <int ENGINE>
-__global__ void __launch_bounds__(BLK) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
+__global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
     __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
@@ -519,7 +522,7 @@ inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 // ================================================= host side ==========================================================
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
 template <class IO>
-static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int* cursor, const int* count_ptr) {
+static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int* cursor, const int* count_ptr) {
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     cudaStream_t st = c->stream;
     if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
@@ -531,6 +534,12 @@ static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int poli
     } else {
         int* sp_count = &c->d_ctrl->special[0]; int* sp_cursor = &c->d_ctrl->special[1];
         constexpr int K = IO::K;
+        if (S.nlist > 0) {
+            // always-test list pre-pass (provisional closest hit / dead shadow rays)
+            if (c->counting) k_trace_list<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, ctr);
+            else k_trace_list<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, ctr);
+            c->launches++;
+        }
         const size_t resident = TraceSmem<K, PTB_TRACE_BLK_S>::fixed + TraceSmem<K, PTB_TRACE_BLK_S>::bvh(S.n);
         if (resident <= (size_t)c->smem_optin && !c->no_resident_bvh) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
@@ -538,12 +547,12 @@ static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int poli
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
             kern<<<c->sm_count, PTB_TRACE_BLK_S, resident, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
         } else {
-            int blocks = IO::kAnyHit ? c->blocks_shadow : c->blocks_extend;
+            int blocks = c->sm_count * 8;
             auto kern = c->counting ? k_trace<IO, true, PTB_TRACE_BLK, false> : k_trace<IO, false, PTB_TRACE_BLK, false>;
             kern<<<blocks, PTB_TRACE_BLK, TraceSmem<K, PTB_TRACE_BLK>::fixed, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
         }
         // rays set aside by the production kernel (axis-parallel / non-finite): exact-test kernel over the (usually empty) list;
-        // its last action resets the list for the next launch
+        // the list is reset for the next launch
         ListedIO<IO> lio{io, c->d_specialq};
         if (c->counting) k_trace_simple<ListedIO<IO>, 1, true><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
         else k_trace_simple<ListedIO<IO>, 1, false><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
@@ -551,6 +560,15 @@ static void launch_trace(ptb_ctx* c, const TraceScene& S, const IO& io, int poli
         c->launches += 2;
     }
     c->launches++;
+}
+// the production policy reads a provisional-hit record when the scene has an always-test list
+static bool use_pre(const TraceScene& S, int policy) { return policy == PTB_TRAVERSE_ORDERED && S.n >= 2 && S.nlist > 0; }
+static void launch_extend(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
+    if (use_pre(S, policy)) launch_trace_io(c, S, ExtendIO<true>{q.o, q.d, c->d_pre, c->st.hit}, policy, cursor, count_ptr);
+    else launch_trace_io(c, S, ExtendIO<false>{q.o, q.d, nullptr, c->st.hit}, policy, cursor, count_ptr);
+}
+static void launch_shadow(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
+    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, cursor, count_ptr);
 }
 
 void ptb_stage_begin(ptb_ctx* c, int stage) {
@@ -583,7 +601,7 @@ int ptb_stage_collect(ptb_ctx* c) {
 int ptb_wf_init(ptb_ctx* c) {
     int64_t np = c->max_paths;
     float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result,
-                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c};
+                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->d_pre};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
     PTB_CUDA(cudaMalloc(&c->d_specialq, sizeof(int) * np));
     PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
@@ -592,15 +610,11 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
     int occ = 0;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ExtendIO, false, PTB_TRACE_BLK, false>, PTB_TRACE_BLK, TraceSmem<2, PTB_TRACE_BLK>::fixed));
-    c->blocks_extend = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace<ShadowIO, false, PTB_TRACE_BLK, false>, PTB_TRACE_BLK, TraceSmem<3, PTB_TRACE_BLK>::fixed));
-    c->blocks_shadow = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO<false>, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO<false>, 0, false>, PTB_TRACE_BLK, 0));
     c->blocks_ref = c->sm_count * (occ > 0 ? occ : 4);
     c->blocks_generic = c->sm_count * 8;
     return 0;
@@ -642,7 +656,7 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     int cur = 0;
     for (int depth = 1; depth <= 5; depth++) {
         ptb_stage_begin(c, ST_EXTEND);
-        { ExtendIO io{c->xq[cur].o, c->xq[cur].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+        launch_extend(c, S, policy, c->xq[cur], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
         ptb_stage_end(c);
         ptb_stage_begin(c, ST_SHADE);
         k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
@@ -651,7 +665,7 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
         c->launches += 1;
         if (ENGINE == PTB_ENGINE_PATH) {
             ptb_stage_begin(c, ST_SHADOW);
-            { ShadowIO io{c->sq.o, c->sq.d, c->sq.c, c->st.result}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow); }
+            launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow);
             ptb_stage_end(c);
         }
         k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
@@ -707,7 +721,7 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
             TraceScene S = ptb_trace_scene(c);
             int policy = ptb_effective_policy(c, c->traversal_request);
             ptb_stage_begin(c, ST_EXTEND);
-            { ExtendIO io{c->xq[0].o, c->xq[0].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+            launch_extend(c, S, policy, c->xq[0], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
             ptb_stage_end(c);
             ptb_stage_begin(c, ST_ACCUM);
             size_t pass = (size_t)c->caps.max_filmsize;
@@ -743,7 +757,7 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
         if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
         TraceScene S = ptb_trace_scene(c);
         int policy = ptb_effective_policy(c, c->traversal_request);
-        { ExtendIO io{c->xq[0].o, c->xq[0].d, c->st.hit}; launch_trace(c, S, io, policy, &c->d_ctrl->cur_extend, &c->d_ctrl->n_in); }
+        launch_extend(c, S, policy, c->xq[0], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
         k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, nullptr, hit_dev, depth_dev, index_dev, uv_dev, 1);
     }
     c->launches += 4;
@@ -760,8 +774,10 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
     k_pack_tap<<<nblk(m), BLK, 0, c->stream>>>(rays_dev, avoid_dev, anyhit ? dis_dev : nullptr, c->d_slot_of, c->nfaces, m, c->sq);
     c->launches += 2;
     int eff = ptb_effective_policy(c, policy);
-    if (anyhit) { TapIO<true> io{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
-    else { TapIO<false> io{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}; launch_trace(c, S, io, eff, &c->d_ctrl->pad[1], &c->d_ctrl->pad[0]); }
+    int* cur = &c->d_ctrl->pad[1]; const int* cnt = &c->d_ctrl->pad[0];
+    if (anyhit) launch_trace_io(c, S, TapIO<true, false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
+    else if (use_pre(S, eff)) launch_trace_io(c, S, TapIO<false, true>{c->sq.o, c->sq.d, c->d_pre, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
+    else launch_trace_io(c, S, TapIO<false, false>{c->sq.o, c->sq.d, nullptr, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
