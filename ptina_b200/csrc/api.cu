@@ -13,7 +13,7 @@ void ptb_set_error(const char* fmt, ...) {
 
 TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
-    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.list = c->d_list; S.nlist = c->list_n; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
+    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.nlo = c->d_nlo; S.nhi = c->d_nhi; S.list = c->d_list; S.nlist = c->list_n; S.scene_abs = c->scene_abs; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
     for (int k = 0; k < 3; k++) { S.root_lo[k] = c->root_lo[k]; S.root_hi[k] = c->root_hi[k]; }
     return S;
 }
@@ -136,7 +136,7 @@ int ptb_destroy(ptb_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
                     c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
-                    c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->d_pre, c->d_specialq,
+                    c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->tq.e[0], c->tq.e[1], c->tq.e[2], c->tq.e[3], c->tq.e[4],
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }

@@ -425,11 +425,17 @@ int ptb_lbvh_build(ptb_ctx* c) {
         int h_scal[16];
         PTB_CUDA(cudaMemcpyAsync(h_scal, c->d_scalars, sizeof h_scal, cudaMemcpyDeviceToHost, st));
         float h_root[6] = {0, 0, 0, 0, 0, 0};
+        float h_troot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (n > 1) {
             PTB_CUDA(cudaMemcpyAsync(h_root, c->d_bmin, 12, cudaMemcpyDeviceToHost, st));
             PTB_CUDA(cudaMemcpyAsync(h_root + 3, c->d_bmax, 12, cudaMemcpyDeviceToHost, st));
+            PTB_CUDA(cudaMemcpyAsync(h_troot, c->d_nlo, 16, cudaMemcpyDeviceToHost, st));
+            PTB_CUDA(cudaMemcpyAsync(h_troot + 4, c->d_nhi, 16, cudaMemcpyDeviceToHost, st));
         }
         PTB_CUDA(cudaStreamSynchronize(st));
+        c->scene_abs = 0.0f;
+        for (int k = 0; k < 6; k++) c->scene_abs = fmaxf(c->scene_abs, fabsf(h_root[k]));
+        if (h_troot[0] <= h_troot[4]) for (int k = 0; k < 3; k++) c->scene_abs = fmaxf(c->scene_abs, fmaxf(fabsf(h_troot[k]), fabsf(h_troot[4 + k])));
         valid = (n > 1) && h_scal[9] == 0;
         depth = valid ? h_scal[10] : 0;
         c->list_n = n > 1 ? h_scal[11] : 0;

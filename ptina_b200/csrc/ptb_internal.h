@@ -33,6 +33,9 @@ struct PathState {
 //   extend : o = (origin, path slot)  d = (unit direction, avoid leaf slot)               -- written by raygen / shade
 //   shadow : o = (origin, path slot)  d = (direction, distance to the light sample)  c = (contribution if unoccluded, avoid leaf slot)
 struct RayQueue { float4* o; float4* d; float4* c; };
+// tree queue (k_trace_pre -> k_trace_tree): 80-byte records, see ptb_trace_kernel.cuh
+#define PTB_EXP_K 5
+struct ExpQ { float4* e[PTB_EXP_K]; };
 
 // device-side control block: queue sizes and work cursors
 struct Ctrl {
@@ -41,8 +44,8 @@ struct Ctrl {
     int n_shadow;    // entries in the shadow queue
     int cur_extend, cur_shadow;
     int pad[3];
-    int special[2];  // rays set aside for the exact-test kernel: count, cursor
-    int pad2[2];
+    int n_tree[2];   // entries of the tree queue written by k_trace_pre: [0] extend, [1] shadow / taps
+    int cur_tree[2];
 };
 
 struct DevCounters {
@@ -95,6 +98,7 @@ struct ptb_ctx {
     float4 *d_nlo = nullptr, *d_nhi = nullptr;   // [n-1] per internal node: traversal box (union of the unlisted leaves below)
     int32_t* d_list = nullptr;      // always-test list (leaf slots), PTB_LIST_CAP entries
     int list_n = 0, list_overflow = 0;
+    float scene_abs = 0.0f;         // largest absolute coordinate of the reference root box and the traversal root box
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)
     ptb_tree_info tree_info{};
@@ -110,8 +114,7 @@ struct ptb_ctx {
     PathState st{};
     RayQueue xq[2]{};               // extend queues (in / out, swapped every bounce)
     RayQueue sq{};                  // shadow queue
-    float4* d_pre = nullptr;        // provisional closest hit over the always-test list, per extend-queue position
-    int* d_specialq = nullptr;      // queue positions of rays the conservative kernel set aside
+    ExpQ tq{};                      // tree queue
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
     int counting = 0;

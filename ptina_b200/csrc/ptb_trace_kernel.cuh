@@ -1,53 +1,56 @@
 // ptb_trace_kernel.cuh -- the traversal kernels.
 //
-//  k_trace       : production kernel.  Persistent warps; every lane owns one ray and keeps its traversal state in registers
-//                  (stack: top entry in a register, the rest in local memory).  Rays arrive as self-contained RECORDS in
-//                  queue order (origin|path, direction|avoid slot, [contribution|tmax]); a warp stages them 32 at a time into a
-//                  double-buffered shared-memory tile with cp.async, so the DRAM latency of the next tile is covered by the
-//                  traversal of the current one.  A lane that finishes its ray takes the next staged record.  Every iteration
-//                  the warp votes for ONE kind of step -- a node step (fetch a 64-B node, two conservative slab tests, push /
-//                  descend) or a leaf step (one triangle test from the lane's ring of pending leaves in shared memory) --
-//                  whichever more lanes can take.  Box tests are conservative (1 FMA per plane); the exact reference test is
-//                  evaluated on the gate box of a triangle that is about to be accepted (ptb_traverse.cuh).  Results are
-//                  bit-identical to trace_reference.
+// Production policy (PTB_TRAVERSE_ORDERED), two kernels per ray queue:
+//  k_trace_pre   : one ray per thread, uniform control flow.  Decodes the queue record, computes the per-ray constants of the
+//                  conservative slab test, tests the always-test list (every thread of a warp tests the same triangle: broadcast
+//                  loads), and tests the root box of the traversal tree.  A ray with nothing left to do (no box of the tree in
+//                  reach -- most rays of a room-like scene) is finished here; the others are appended, as self-contained 80-byte
+//                  records, to the tree queue.  Axis-parallel / non-finite rays, which the conservative test cannot handle, are
+//                  traced here with the exact routine (trace_ordered).
+//  k_trace_tree  : persistent warps, one ray per lane, traversal state in registers (stack: top entry in a register, the rest in
+//                  local memory).  A warp stages the records of the tree queue 16 at a time into a double-buffered shared-memory
+//                  tile with cp.async, so the DRAM latency of the next tile is covered by the traversal of the current one; a lane
+//                  that finishes its ray takes the next staged record.  Every iteration the warp votes for ONE kind of step -- a
+//                  node step (fetch a 64-B node, two conservative slab tests, push / descend) or a leaf step (gate test + triangle
+//                  test from the lane's ring of pending leaves in shared memory) -- whichever more lanes can take.  For scenes
+//                  whose packed BVH fits, each CTA keeps it resident in shared memory (SMEM variant).
+//  Box tests are conservative (1 FMA per plane); the exact reference test is evaluated on the gate box of a triangle that is about
+//  to be accepted and that the conservative bounds cannot decide (ptb_traverse.cuh).  Results are bit-identical to trace_reference.
+//
 //  k_trace_simple: one ray per thread.  POLICY 0 = the reference's literal traversal (lbvh.py:313-347): used when the tree is not a
 //                  proper tree, when PTB_TRAVERSE_REFERENCE is requested, and by the tests as the on-device checker.
-//                  POLICY 1 = trace_ordered (exact slab test at every node): traces the rays k_trace sets aside (axis-parallel /
-//                  non-finite) and is the PTB_TRAVERSE_ORDERED_EXACT checker.
+//                  POLICY 1 = trace_ordered (exact slab test at every node): the PTB_TRAVERSE_ORDERED_EXACT checker.
 #pragma once
 #include "ptb_internal.h"
 
 #define PTB_TRACE_BLK 128
-#define PTB_TILE 32                 /* ray records per staged tile (one per lane) */
+#define PTB_TILE 16                 /* ray records per staged tile */
 #ifndef PTB_FETCH_MIN
-#define PTB_FETCH_MIN 6             /* idle lanes that trigger a refill from the staged tile */
+#define PTB_FETCH_MIN 8             /* idle lanes that trigger a refill from the staged tile */
 #endif
 
-struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; float4 pre; bool dead; };
+struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; };
 
-// Record formats (float4 arrays indexed by queue position):
-//   q0 = (origin, path slot)                                                               -- every queue
-//   q1 = (unit direction, avoid leaf slot)                 extend   |  (direction, distance to the light sample)   shadow
-//   q2 = provisional closest hit over the always-test list  extend  |  (contribution if unoccluded, avoid leaf slot) shadow
-//        (depth, u, v, leaf slot or -1; written by k_trace_list, present iff PRE)
-// A shadow record whose distance is negative is dead: k_trace_list found an occluder in the always-test list.
+// Queue records (float4 arrays indexed by queue position), written by raygen / shade / k_pack_tap:
+//   q0 = (origin, path slot)
+//   q1 = (unit direction, avoid leaf slot)   extend   |  (direction, distance to the light sample)                  shadow
+//   q2 =  --                                          |  (contribution if unoccluded, avoid leaf slot)               shadow
+// Tree-queue records (ExpQ, written by k_trace_pre):
+//   e0 = (origin, path slot)  e1 = (direction, avoid leaf slot)  e2 = (1/d, delta)  e3 = (-o/d, -)
+//   e4 = provisional closest hit over the always-test list (depth, u, v, leaf slot or -1)   extend
+//      = (contribution if unoccluded, distance to the light sample)                            shadow
 
 // ---- extend queue: closest hit for path p (path.py:28-29) ---------------------------------------------------------------------------
-template <bool PRE>
 struct ExtendIO {
     static constexpr bool kAnyHit = false;
-    static constexpr bool kPre = PRE;
-    static constexpr int K = PRE ? 3 : 2;
-    const float4* __restrict__ q0; const float4* __restrict__ q1; float4* q2; float4* hit;
-    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
+    static constexpr int K = 2;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; float4* hit;
+    PTB_D const float4* rec(int k) const { return k == 0 ? q0 : q1; }
     PTB_D void decode(const float4* r, RayIn* in) const {
         in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
-        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->avoid_slot = __float_as_int(r[1].w); in->tmax = PTB_INF;
-        if (PRE) in->pre = r[K - 1];
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->avoid_slot = __float_as_int(r[1].w); in->tmax = PTB_INF; in->c = v3s(0.0f);
     }
     PTB_D void store(int p, const HitRec& h, V3) const { hit[p] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.index : -1)); }
-    PTB_D void store_pre(int idx, const HitRec& h, bool) const { q2[idx] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.slot : -1)); }
-    PTB_D void store_dead(int) const {}
 };
 // ---- shadow queue: Ray(hitpos, li.dir) against avoid = hit triangle; unoccluded -> add the pending contribution (path.py:49-55).
 // The direction is used as sampled (not re-normalised, like the reference).  Exactly one shadow ray per path per launch touches
@@ -55,13 +58,12 @@ struct ExtendIO {
 // for the load.
 struct ShadowIO {
     static constexpr bool kAnyHit = true;
-    static constexpr bool kPre = false;
     static constexpr int K = 3;
-    const float4* __restrict__ q0; float4* q1; const float4* __restrict__ q2; float4* result;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2; float4* result;
     PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
     PTB_D void decode(const float4* r, RayIn* in) const {
         in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
-        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->tmax = r[1].w; in->dead = r[1].w < 0.0f;
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->tmax = r[1].w;
         in->c = mk3(r[2].x, r[2].y, r[2].z); in->avoid_slot = __float_as_int(r[2].w);
     }
     PTB_D void store(int p, const HitRec& h, V3 c) const {
@@ -69,59 +71,33 @@ struct ShadowIO {
         float* r = reinterpret_cast<float*>(&result[p]);
         atomicAdd(r, c.x); atomicAdd(r + 1, c.y); atomicAdd(r + 2, c.z);
     }
-    PTB_D void store_pre(int idx, const HitRec&, bool occluded) const { if (occluded) q1[idx].w = -1.0f; }
-    PTB_D void store_dead(int) const {}
 };
 // ---- parity taps: the same record formats (written by k_pack_tap), results into flat arrays -------------------------------------------
-template <bool ANYHIT, bool PRE>
+template <bool ANYHIT>
 struct TapIO {
     static constexpr bool kAnyHit = ANYHIT;
-    static constexpr bool kPre = PRE && !ANYHIT;
-    static constexpr int K = (ANYHIT || PRE) ? 3 : 2;
-    const float4* __restrict__ q0; float4* q1; float4* q2;
+    static constexpr int K = ANYHIT ? 3 : 2;
+    const float4* __restrict__ q0; const float4* __restrict__ q1; const float4* __restrict__ q2;
     int* hit; float* depth; int* index; float* uv;
     PTB_D const float4* rec(int k) const { return k == 0 ? q0 : (k == 1 ? q1 : q2); }
     PTB_D void decode(const float4* r, RayIn* in) const {
         in->item = __float_as_int(r[0].w); in->ro = mk3(r[0].x, r[0].y, r[0].z);
-        in->rd = mk3(r[1].x, r[1].y, r[1].z);
-        if (ANYHIT) { in->tmax = r[1].w; in->dead = r[1].w < 0.0f; in->avoid_slot = __float_as_int(r[K - 1].w); }
-        else { in->tmax = PTB_INF; in->avoid_slot = __float_as_int(r[1].w); if (PRE) in->pre = r[K - 1]; }
+        in->rd = mk3(r[1].x, r[1].y, r[1].z); in->c = v3s(0.0f);
+        if (ANYHIT) { in->tmax = r[1].w; in->avoid_slot = __float_as_int(r[K - 1].w); }
+        else { in->tmax = PTB_INF; in->avoid_slot = __float_as_int(r[1].w); }
     }
     PTB_D void store(int i, const HitRec& h, V3) const {
         hit[i] = h.hit;
         if (!ANYHIT) { depth[i] = h.depth; index[i] = h.index; uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
     }
-    PTB_D void store_pre(int idx, const HitRec& h, bool occluded) const {
-        if (ANYHIT) { if (occluded) q1[idx].w = -1.0f; }
-        else q2[idx] = make_float4(h.depth, h.u, h.v, __int_as_float(h.hit ? h.slot : -1));
-    }
-    PTB_D void store_dead(int i) const { hit[i] = 1; }
-};
-// ---- rays the production kernel set aside (axis-parallel / non-finite): queue positions listed in `list` -----------------------
-template <class IO>
-struct ListedIO {
-    static constexpr bool kAnyHit = IO::kAnyHit;
-    static constexpr int K = IO::K;
-    IO io; const int* __restrict__ list;
-};
-template <class IO> struct IOTraits {
-    PTB_D static int position(const IO&, int i) { return i; }
-    PTB_D static const IO& base(const IO& io) { return io; }
-};
-template <class IO> struct IOTraits<ListedIO<IO>> {
-    PTB_D static int position(const ListedIO<IO>& l, int i) { return l.list[i]; }
-    PTB_D static const IO& base(const ListedIO<IO>& l) { return l.io; }
 };
 
 // record `i` of the queue straight from global memory (one-ray-per-thread kernels)
 template <class IO>
-PTB_D void fetch_direct(const IO& io_any, int i, RayIn* in) {
-    const auto& io = IOTraits<IO>::base(io_any);
-    const int pos = IOTraits<IO>::position(io_any, i);
+PTB_D void fetch_direct(const IO& io, int i, RayIn* in) {
     float4 r[IO::K];
 #pragma unroll
-    for (int k = 0; k < IO::K; k++) r[k] = io.rec(k)[pos];
-    in->c = v3s(0.0f); in->dead = false; in->pre = make_float4(PTB_INF, 0.0f, 0.0f, __int_as_float(-1));
+    for (int k = 0; k < IO::K; k++) r[k] = io.rec(k)[i];
     io.decode(r, in);
 }
 
@@ -158,63 +134,94 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO
             fetch_direct(io, idx, &in);
             const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
             HitRec h;
-            if (in.dead) { h.hit = 1; h.depth = 0.0f; h.index = -1; h.u = h.v = 0.0f; h.slot = -1; }     // occluded by the always-test list
-            else if (POLICY == 0) {
+            if (POLICY == 0) {
                 h = trace_reference<COUNT>(S, in.ro, in.rd, avoid, &C);
                 if (IO::kAnyHit) h.hit = !(h.hit == 0 || h.depth > in.tmax);       // path.py:50  occ.hit == 0 or occ.depth > li.dis
             } else {
                 h = trace_ordered<IO::kAnyHit, COUNT>(S, in.ro, in.rd, avoid, in.tmax, &C);
             }
-            IOTraits<IO>::base(io).store(in.item, h, in.c);
+            io.store(in.item, h, in.c);
             if (COUNT) nrays++;
         }
     }
     flush_counters<COUNT>(C, nrays, IO::kAnyHit, ctr);
 }
 
-// ---- always-test list pre-pass: one ray per thread, every thread of a warp tests the same triangle (broadcast loads, no
-// divergence in the loop).  Extend: writes the provisional closest hit over the list (q2).  Shadow: marks occluded rays dead.
-// Axis-parallel / non-finite rays are left untouched (k_trace sets them aside for k_trace_simple<1>, which tests every triangle).
+// ---- production phase A: per-ray setup, always-test list, root test; survivors go to the tree queue ---------------------------------
 template <class IO, bool COUNT>
-__global__ void __launch_bounds__(256) k_trace_list(TraceScene S, IO io, const int* count_ptr, DevCounters* ctr) {
+__global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const int* count_ptr, ExpQ xq, int* tree_count, DevCounters* ctr) {
     constexpr bool ANYHIT = IO::kAnyHit;
     const int count = *count_ptr;
-    unsigned long long ntris = 0;
-    for (int idx = blockIdx.x * 256 + threadIdx.x; idx < count; idx += gridDim.x * 256) {
-        RayIn in;
-        fetch_direct(io, idx, &in);
+    const int lane = threadIdx.x & 31;
+    TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
+    unsigned long long nrays = 0;
+    const int rounded = (count + 31) & ~31;
+    for (int idx = blockIdx.x * 256 + threadIdx.x; idx < rounded; idx += gridDim.x * 256) {
+        bool live = false;
+        RayIn in; in.item = -1; in.ro = v3s(0.0f); in.rd = v3s(0.0f); in.avoid_slot = -1; in.tmax = 0.0f; in.c = v3s(0.0f);
+        RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
+        float delta = 0.0f;
         HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-        bool occluded = false;
-        if (!ray_is_special(in.ro, in.rd)) {
-            const RayCons R = ray_cons(in.ro, in.rd);
-            float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
-            for (int j = 0; j < S.nlist; j++) {
-                const int slot = S.list[j];
-                if (slot == in.avoid_slot) continue;
-                const Tri64 T = S.tris[slot];
-                if (COUNT) ntris++;
-                float dep, s, t;
-                if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
-                    const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
-                    if (better) {
-                        // the reference tests this triangle only if its gate passes Box.intersect: conservative, exact when grazing
-                        const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
-                        float gl; bool gsure;
-                        if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], in.ro, in.rd))) {
-                            ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep;
-                            if (ANYHIT) { occluded = true; break; }
+        if (idx < count) {
+            fetch_direct(io, idx, &in);
+            if (COUNT) nrays++;
+            if (ray_is_special(in.ro, in.rd)) {
+                // axis-parallel / non-finite: exact tests over the reference's own arrays (rare)
+                const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
+                ret = trace_ordered<ANYHIT, COUNT>(S, in.ro, in.rd, avoid, in.tmax, &C);
+                io.store(in.item, ret, in.c);
+            } else {
+                R = ray_cons(in.ro, in.rd);
+                float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
+                bool occluded = false;
+                for (int j = 0; j < S.nlist; j++) {
+                    const int slot = S.list[j];
+                    if (slot == in.avoid_slot) continue;
+                    const Tri64 T = S.tris[slot];
+                    if (COUNT) C.tris++;
+                    float dep, s, t;
+                    if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
+                        const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+                        if (better) {
+                            // the reference tests this triangle only if its gate passes Box.intersect: conservative, exact when grazing
+                            const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
+                            float gl; bool gsure;
+                            if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], in.ro, in.rd))) {
+                                ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep;
+                                if (ANYHIT) { occluded = true; break; }
+                            }
                         }
                     }
                 }
+                // anything left in the tree?  its root box = union of the inflated bounds of every triangle not in the list
+                if (!occluded && S.n >= 2) {
+                    float lb;
+                    if (COUNT) C.boxes++;
+                    delta = trav_delta(in.ro, S.scene_abs);
+                    const RayTrav Q = ray_trav(R, delta);
+                    live = S.nlo[0].x <= S.nhi[0].x && slab_trav(S.nlo[0], S.nhi[0], R, Q, &lb) && !(lb > best + best * PTB_CULL_GUARD);
+                }
+                if (!live) {
+                    if (ret.hit) ret.index = S.leaf[ret.slot];
+                    io.store(in.item, ret, in.c);
+                }
             }
         }
-        IOTraits<IO>::base(io).store_pre(idx, ret, occluded);
+        // append the survivors to the tree queue: one atomic per warp, contiguous records
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(tree_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            xq.e[0][pos] = make_float4(in.ro.x, in.ro.y, in.ro.z, __int_as_float(in.item));
+            xq.e[1][pos] = make_float4(in.rd.x, in.rd.y, in.rd.z, __int_as_float(in.avoid_slot));
+            xq.e[2][pos] = make_float4(R.r.x, R.r.y, R.r.z, delta);
+            xq.e[3][pos] = make_float4(R.nc.x, R.nc.y, R.nc.z, 0.0f);
+            xq.e[4][pos] = ANYHIT ? make_float4(in.c.x, in.c.y, in.c.z, in.tmax) : make_float4(ret.depth, ret.u, ret.v, __int_as_float(ret.hit ? ret.slot : -1));
+        }
     }
-    if (COUNT) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ntris += __shfl_xor_sync(0xffffffffu, ntris, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&ctr->tris, ntris);
-    }
+    flush_counters<COUNT>(C, nrays, ANYHIT, ctr);
 }
 
 // ---- cp.async helpers (16-byte global -> shared copies, per-thread groups) --------------------------------------------------------------
@@ -229,75 +236,76 @@ template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group 
 #ifndef PTB_NODE_REPS
 #define PTB_NODE_REPS 1             /* node steps per vote */
 #endif
+#ifndef PTB_TRACE_BLK_S
 #define PTB_TRACE_BLK_S 768         /* threads of the shared-memory-resident variant (one CTA per SM) */
+#endif
+#ifndef PTB_TRACE_MINB
+#define PTB_TRACE_MINB 8            /* resident CTAs per SM the global-memory variant is compiled for */
+#endif
 
-// dynamic shared memory layout of k_trace (bytes), shared by the kernel and the host launch code
-template <int K, int BLK>
+// dynamic shared memory layout of k_trace_tree (bytes), shared by the kernel and the host launch code
+template <int BLK>
 struct TraceSmem {
-    static constexpr size_t tile = (size_t)(BLK / 32) * 2 * K * PTB_TILE * sizeof(float4);
+    static constexpr size_t tile = (size_t)(BLK / 32) * 2 * PTB_EXP_K * PTB_TILE * sizeof(float4);
     static constexpr size_t queue = (size_t)PTB_PQ * BLK * (sizeof(int) + sizeof(float));
     static constexpr size_t fixed = tile + queue;
-    __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64) + (size_t)n * sizeof(Tri64); }
+    __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64); }
 };
 
-// ---- production kernel -------------------------------------------------------------------------------------------------------------------
-// SMEM = true: the whole packed BVH (nodes + triangles, 128 B per triangle) is copied into shared memory by each CTA (one CTA of
-// PTB_TRACE_BLK_S threads per SM) as four 16-byte "quarter" arrays per record type, so that a divergent 64-byte fetch costs ~4 x 7
-// shared-memory wavefronts instead of 4 x 32 L1 wavefronts (one per lane and 16-byte load) -- for incoherent rays the L1 wavefront
-// rate, not the issue rate, is what binds the global-memory variant.  Used when the BVH fits (ptb_wf: n <= ~1400 triangles).
+// ---- production phase B: traversal of the tree for the rays k_trace_pre queued ----------------------------------------------------
+// SMEM = true: the packed nodes of the traversal tree (64 B per triangle) are copied into shared memory by each CTA (one CTA of
+// PTB_TRACE_BLK_S threads per SM) as four 16-byte "quarter" arrays, so that a divergent 64-byte node fetch costs ~4 x 7
+// shared-memory wavefronts instead of 4 x 32 L1 wavefronts (one per lane and 16-byte load).  Triangles, gate boxes and the
+// local-memory stack stay behind L1, which keeps ~100 KB next to the 150 KB carve-out.
 template <class IO, bool COUNT, int BLK, bool SMEM>
-__global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io, int* cursor, const int* count_ptr, int* __restrict__ special_list, int* special_count,
-                                                             DevCounters* ctr) {
+__global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(TraceScene S, IO io, ExpQ xq, int* cursor, const int* count_ptr, DevCounters* ctr) {
     constexpr bool ANYHIT = IO::kAnyHit;
-    constexpr int K = IO::K;
+    constexpr int K = PTB_EXP_K;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int WARPS = BLK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int count = *count_ptr;
     const int n = S.n;
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
-    unsigned long long nrays = 0;
 
     extern __shared__ __align__(16) unsigned char s_raw[];
-    // staged ray records: [warp][buffer][k][lane]
+    // staged ray records: [warp][buffer][k][record]
     float4 (*s_tile)[2][K][PTB_TILE] = reinterpret_cast<float4 (*)[2][K][PTB_TILE]>(s_raw);
-    // pending leaves: ring of PTB_PQ (slot, lower bound of the entry distance) per lane, column = thread (no bank conflicts)
-    int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + TraceSmem<K, BLK>::tile);
-    float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + TraceSmem<K, BLK>::tile + (size_t)PTB_PQ * BLK * sizeof(int));
-    // resident BVH: quarter q of node i at s_node[q * (n-1) + i], quarter q of triangle s at s_tri[q * n + s]
-    float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<K, BLK>::fixed);
-    float4* s_tri = s_node + 4 * (size_t)(n - 1);
+    // pending leaves: ring of PTB_PQ (slot, lower bound of the depth) per lane, column = thread (no bank conflicts)
+    int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + TraceSmem<BLK>::tile);
+    float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + TraceSmem<BLK>::tile + (size_t)PTB_PQ * BLK * sizeof(int));
+    // resident nodes: quarter q of node i at s_node[q * (n-1) + i]
+    float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<BLK>::fixed);
     if (SMEM) {
+        if (blockIdx.x * PTB_TILE >= count) return;        // more CTAs than tiles of work: skip the copy
         const float4* gn = reinterpret_cast<const float4*>(S.nodes);
-        const float4* gt = reinterpret_cast<const float4*>(S.tris);
         for (int i = threadIdx.x; i < 4 * (n - 1); i += BLK) s_node[(i & 3) * (n - 1) + (i >> 2)] = gn[i];
-        for (int i = threadIdx.x; i < 4 * n; i += BLK) s_tri[(i & 3) * n + (i >> 2)] = gt[i];
         __syncthreads();
     }
 
     // ---- warp-uniform staging state ----
-    int tile_base0 = 0, tile_base1 = 0, tile_n0 = 0, tile_n1 = 0;   // queue position of record 0 / number of valid records, per buffer
-    int cur_buf = 0, tile_pos = 0;                                   // consumption cursor in the current buffer
+    int tile_n0 = 0, tile_n1 = 0;              // number of valid records per buffer
+    int cur_buf = 0, tile_pos = 0;             // consumption cursor in the current buffer
     bool tile_ready = false, exhausted = false;
     auto fill = [&](int b) {
         int base = 0;
         if (lane == 0) base = atomicAdd(cursor, PTB_TILE);
         base = __shfl_sync(FULL, base, 0);
         const int nv = max(0, min(PTB_TILE, count - base));
-        if (lane < nv) {
 #pragma unroll
-            for (int k = 0; k < K; k++) cp_async16(&s_tile[warp][b][k][lane], io.rec(k) + base + lane);
+        for (int e = lane; e < K * PTB_TILE; e += 32) {
+            const int k = e / PTB_TILE, i = e % PTB_TILE;
+            if (i < nv) cp_async16(&s_tile[warp][b][k][i], xq.e[k] + base + i);
         }
         cp_async_commit();
-        if (b == 0) { tile_base0 = base; tile_n0 = nv; } else { tile_base1 = base; tile_n1 = nv; }
+        if (b == 0) tile_n0 = nv; else tile_n1 = nv;
     };
     fill(0); fill(1);
 
     // ---- per-lane ray state ----
     int item = -1, avoid_slot = -1;            // item >= 0: this lane owns a ray (its result is stored when the lane next goes idle)
     RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
-    float kL = 0.0f, aL = 0.0f;                // margins of the traversal-tree boxes (leaf_margins)
+    RayTrav Q; Q.nc1 = v3s(0.0f); Q.nc2 = v3s(0.0f);   // slab constants of the traversal-tree boxes (ray_trav)
     V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
@@ -326,31 +334,23 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
             if (me && item >= 0) { io.store(item, ret, contrib); item = -1; }
             const int k = tile_pos + __popc(idle & lt_mask);
             if (me && k < nv) {
-                float4 r[K];
-#pragma unroll
-                for (int j = 0; j < K; j++) r[j] = s_tile[warp][cur_buf][j][k];
-                RayIn in; in.c = v3s(0.0f); in.dead = false;
-                io.decode(r, &in);
-                if (ray_is_special(in.ro, in.rd)) {
-                    special_list[atomicAdd(special_count, 1)] = (cur_buf == 0 ? tile_base0 : tile_base1) + k;    // traced by k_trace_simple<1> afterwards (rare)
-                } else if (in.dead) {                                      // occluded by the always-test list: nothing to trace
-                    io.store_dead(in.item);
-                } else {
-                    if (COUNT) nrays++;
-                    item = in.item; avoid_slot = in.avoid_slot; contrib = in.c;
-                    R = ray_cons(in.ro, in.rd);
-                    leaf_margins(R, &kL, &aL);
-                    ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-                    if (IO::kPre) {                                         // provisional closest hit over the always-test list
-                        ret.slot = __float_as_int(in.pre.w); ret.hit = ret.slot >= 0;
-                        ret.depth = in.pre.x; ret.u = in.pre.y; ret.v = in.pre.z;
-                        if (ret.hit) ret.index = S.leaf[ret.slot];
-                    }
-                    best = ANYHIT ? fminf(in.tmax, PTB_INF) : ret.depth;
-                    cull = best + best * PTB_CULL_GUARD;
-                    sp = 0; cur_near = 0.0f; q_head = 0; q_count = 0;
-                    cur = 0;            // the root (its children's boxes are tested in its node step)
+                const float4 e0 = s_tile[warp][cur_buf][0][k], e1 = s_tile[warp][cur_buf][1][k], e2 = s_tile[warp][cur_buf][2][k],
+                             e3 = s_tile[warp][cur_buf][3][k], e4 = s_tile[warp][cur_buf][4][k];
+                item = __float_as_int(e0.w); avoid_slot = __float_as_int(e1.w);
+                R.o = mk3(e0.x, e0.y, e0.z); R.d = mk3(e1.x, e1.y, e1.z); R.r = mk3(e2.x, e2.y, e2.z); R.nc = mk3(e3.x, e3.y, e3.z);
+                R.a2 = __fmaf_rn(fmaxf(fmaxf(fabsf(R.nc.x), fabsf(R.nc.y)), fabsf(R.nc.z)), PTB_CONS_KAPPA, 1e-30f);
+                Q = ray_trav(R, e2.w);
+                ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
+                if (ANYHIT) { contrib = mk3(e4.x, e4.y, e4.z); best = fminf(e4.w, PTB_INF); }
+                else {                                                      // provisional closest hit over the always-test list
+                    ret.slot = __float_as_int(e4.w); ret.hit = ret.slot >= 0;
+                    ret.depth = e4.x; ret.u = e4.y; ret.v = e4.z;
+                    if (ret.hit) ret.index = S.leaf[ret.slot];
+                    best = ret.depth;
                 }
+                cull = best + best * PTB_CULL_GUARD;
+                sp = 0; cur_near = 0.0f; q_head = 0; q_count = 0;
+                cur = 0;                // the root (its children's boxes are tested in its node step)
             }
             tile_pos = min(tile_pos + __popc(idle), nv);
             if (tile_pos >= nv && !exhausted) {        // tile consumed: switch to the prefetched one and refill this buffer
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
                     if (COUNT) { C.nodes++; C.boxes += 2; }
                     const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);      // -1: nothing below
                     float n0, n1;
-                    const bool h0 = slab_trav(N.a, N.b, R, kL, aL, &n0) && !(n0 > cull) && c0 >= 0;
-                    const bool h1 = slab_trav(N.c, N.d, R, kL, aL, &n1) && !(n1 > cull) && c1 >= 0;
+                    const bool h0 = slab_trav(N.a, N.b, R, Q, &n0) && !(n0 > cull) && c0 >= 0;
+                    const bool h1 = slab_trav(N.c, N.d, R, Q, &n1) && !(n1 > cull) && c1 >= 0;
                     const bool leaf0 = c0 < n, leaf1 = c1 < n;
                     const bool p0 = h0 && leaf0 && c0 != avoid_slot, p1 = h1 && leaf1 && c1 != avoid_slot;
                     if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c0; s_qnear[k][threadIdx.x] = n0; q_count++; }
@@ -405,13 +405,10 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
                 q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
                 if (!(lnear > cull)) {
                     // the reference tests this triangle only if its gate box passes Box.intersect: conservative test first
-                    float4 glo, ghi;
-                    glo = S.gbox[2 * slot]; ghi = S.gbox[2 * slot + 1];
+                    const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
                     float gl; bool gsure;
                     if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure)) {
-                        Tri64 T;
-                        if (SMEM) { T.a = s_tri[slot]; T.b = s_tri[n + slot]; T.c = s_tri[2 * n + slot]; T.d = s_tri[3 * n + slot]; }
-                        else T = S.tris[slot];
+                        const Tri64 T = S.tris[slot];
                         if (COUNT) C.tris++;
                         float dep, s, t;
                         if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
@@ -431,5 +428,5 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : 8) k_trace(TraceScene S, IO io
     }
     if (item >= 0) io.store(item, ret, contrib);
     cp_async_wait<0>();
-    flush_counters<COUNT>(C, nrays, ANYHIT, ctr);
+    flush_counters<COUNT>(C, 0ull, ANYHIT, ctr);
 }

@@ -33,6 +33,9 @@ struct TraceScene {
     const int* __restrict__ slot_of;     // [n]  face id -> slot      (inverse of leaf, proper trees only)
     const int* __restrict__ gate;        // [n]  slot -> internal node whose child the leaf is (its box gates the triangle test)
     const float4* __restrict__ gbox;     // [2n] slot -> reference box (lo, hi) of its gate
+    const float4* __restrict__ nlo;      // [n-1] traversal boxes of the internal nodes (lo, hi); [0] = the root's
+    const float4* __restrict__ nhi;
+    float scene_abs;                     // largest absolute coordinate of the (inflated) scene bounds
     const int* __restrict__ list;        // always-test list (leaf slots): big or ill-conditioned triangles kept out of the traversal tree
     int nlist;
     // reference arrays (lbvh.py:50-59) for the literal traversal
@@ -185,27 +188,33 @@ PTB_D bool slab_cons2(float lox, float loy, float loz, float hix, float hiy, flo
 // but bounds every node by the union of the INFLATED bounds of the triangles below it -- inflated by eps_T, the distance within
 // which the f32 arithmetic of Face.intersect can accept a point outside the triangle (lbvh.cu k_tri_prep) -- and leaves
 // out triangles that would spoil it: big ones (their bounds make every ancestor's box huge) and ill-conditioned ones (no usable
-// eps_T) go to a short always-test list.  The ray-side part of the bound: if T is accepted at depth r then the real point
-// ro + r*rd lies within eps_T + 64u(|ro|_1 + r|rd|_1) of T's bounds, i.e. r lies in the slab interval of the inflated box widened by
-// 64u(|ro|_1 + r|rd|_1) * max|1/d|.  leaf_margins() turns that (plus the rounding of the 1-FMA slab arithmetic) into the relative /
-// absolute margins (kL, aL) used for every box of the traversal tree.
-PTB_D void leaf_margins(const RayCons& R, float* kL, float* aL) {
+// eps_T) go to a short always-test list.
+// Ray side of the bound: if T is accepted at depth r, the real point X = ro + r*rd lies within eps_T + delta of T's bounds on every
+// axis, delta = 64u(|ro|_1 + r|rd|_1).  Since X is then within eps_T + delta of the scene, r|rd_a| <= S + |o_a| per axis (S = largest
+// absolute coordinate of the inflated scene), which bounds delta by the per-ray constant 65u(2|ro|_1 + 3S) -- no r left in it.
+// A spatial slack delta on axis a moves that axis' slab interval by delta*|1/d_a| at both ends: folded, with the right sign, into
+// the two FMA constants  nc1 = -o/d - delta/d  (lo planes)  and  nc2 = -o/d + delta/d  (hi planes).  The rounding of the 1-FMA
+// arithmetic itself is covered by the relative margin 8u and the absolute margin a2, as for the gate test.
+struct RayTrav { V3 nc1, nc2; };
+PTB_D float trav_delta(V3 o, float scene_abs) {
     const float U = 5.9604644775390625e-8f;
-    const float rmax = fmaxf(fmaxf(fabsf(R.r.x), fabsf(R.r.y)), fabsf(R.r.z));
-    const float d1 = fabsf(R.d.x) + fabsf(R.d.y) + fabsf(R.d.z), o1 = fabsf(R.o.x) + fabsf(R.o.y) + fabsf(R.o.z);
-    *kL = 8.0f * U + 160.0f * U * d1 * rmax;
-    *aL = R.a2 + 160.0f * U * o1 * rmax;
+    return 65.0f * U * (2.0f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z)) + 3.0f * scene_abs);
 }
-// slab test of a traversal-tree box with margins (k, a): false only if no triangle below can be accepted; *lb <= depth of
-// anything accepted below.
-PTB_D bool slab_trav(float4 lo, float4 hi, const RayCons& R, float k, float a, float* lb) {
-    const float x1 = __fmaf_rn(lo.x, R.r.x, R.nc.x), x2 = __fmaf_rn(hi.x, R.r.x, R.nc.x);
-    const float y1 = __fmaf_rn(lo.y, R.r.y, R.nc.y), y2 = __fmaf_rn(hi.y, R.r.y, R.nc.y);
-    const float z1 = __fmaf_rn(lo.z, R.r.z, R.nc.z), z2 = __fmaf_rn(hi.z, R.r.z, R.nc.z);
+PTB_D RayTrav ray_trav(const RayCons& R, float delta) {
+    RayTrav Q;
+    Q.nc1 = mk3(__fmaf_rn(-delta, R.r.x, R.nc.x), __fmaf_rn(-delta, R.r.y, R.nc.y), __fmaf_rn(-delta, R.r.z, R.nc.z));
+    Q.nc2 = mk3(__fmaf_rn(delta, R.r.x, R.nc.x), __fmaf_rn(delta, R.r.y, R.nc.y), __fmaf_rn(delta, R.r.z, R.nc.z));
+    return Q;
+}
+// slab test of a traversal-tree box: false only if no triangle below can be accepted; *lb <= depth of anything accepted below.
+PTB_D bool slab_trav(float4 lo, float4 hi, const RayCons& R, const RayTrav& Q, float* lb) {
+    const float x1 = __fmaf_rn(lo.x, R.r.x, Q.nc1.x), x2 = __fmaf_rn(hi.x, R.r.x, Q.nc2.x);
+    const float y1 = __fmaf_rn(lo.y, R.r.y, Q.nc1.y), y2 = __fmaf_rn(hi.y, R.r.y, Q.nc2.y);
+    const float z1 = __fmaf_rn(lo.z, R.r.z, Q.nc1.z), z2 = __fmaf_rn(hi.z, R.r.z, Q.nc2.z);
     const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
     const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
-    const float l = __fmaf_rn(-tn, k, tn) - a;
-    const float ub = __fmaf_rn(fabsf(tf), k, tf);
+    const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -R.a2);
+    const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
     *lb = l;
     return !(l > ub);
 }

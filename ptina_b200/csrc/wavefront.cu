@@ -86,10 +86,9 @@ __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, 
     }
 }
 
-__global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
-__global__ void k_ctrl_special(Ctrl* c) { c->special[0] = 0; c->special[1] = 0; }
-__global__ void k_ctrl_tap(Ctrl* c, int m) { c->pad[0] = m; c->pad[1] = 0; }
-__global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; }
+__global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; c->n_tree[0] = c->n_tree[1] = 0; c->cur_tree[0] = c->cur_tree[1] = 0; }
+__global__ void k_ctrl_tap(Ctrl* c, int m) { c->pad[0] = m; c->pad[1] = 0; c->n_tree[1] = 0; c->cur_tree[1] = 0; }
+__global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; c->n_tree[0] = c->n_tree[1] = 0; c->cur_tree[0] = c->cur_tree[1] = 0; }
 
 // ---- path.py:85-93 do_render (first half) / brute.py:66-73 -----------------------------------------------------------
 // renorm: path_trace normalises the (already unit) camera direction again before intersecting (path.py:28); PreviewEngine does not
@@ -147,7 +146,7 @@ PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict_
 
 // ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
 #ifndef PTB_SHADE_MINBLOCKS
-#define PTB_SHADE_MINBLOCKS 1
+#define PTB_SHADE_MINBLOCKS 8
 #endif
 template <int ENGINE>
 __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
@@ -521,8 +520,9 @@ inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 
 // ================================================= host side ==========================================================
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
+// which: 0 = extend, 1 = shadow / taps (selects the tree-queue counters of the control block, reset by k_ctrl_*)
 template <class IO>
-static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int* cursor, const int* count_ptr) {
+static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int which, int* cursor, const int* count_ptr) {
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     cudaStream_t st = c->stream;
     if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
@@ -532,43 +532,30 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
         if (c->counting) k_trace_simple<IO, 1, true><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
         else k_trace_simple<IO, 1, false><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
     } else {
-        int* sp_count = &c->d_ctrl->special[0]; int* sp_cursor = &c->d_ctrl->special[1];
-        constexpr int K = IO::K;
-        if (S.nlist > 0) {
-            // always-test list pre-pass (provisional closest hit / dead shadow rays)
-            if (c->counting) k_trace_list<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, ctr);
-            else k_trace_list<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, ctr);
-            c->launches++;
-        }
-        const size_t resident = TraceSmem<K, PTB_TRACE_BLK_S>::fixed + TraceSmem<K, PTB_TRACE_BLK_S>::bvh(S.n);
+        int* n_tree = &c->d_ctrl->n_tree[which]; int* cur_tree = &c->d_ctrl->cur_tree[which];
+        // phase A: per-ray setup, always-test list, root test; survivors -> tree queue
+        if (c->counting) k_trace_pre<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
+        else k_trace_pre<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
+        // phase B: tree traversal of the survivors
+        const size_t resident = TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n);
         if (resident <= (size_t)c->smem_optin && !c->no_resident_bvh) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
-            auto kern = c->counting ? k_trace<IO, true, PTB_TRACE_BLK_S, true> : k_trace<IO, false, PTB_TRACE_BLK_S, true>;
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
-            kern<<<c->sm_count, PTB_TRACE_BLK_S, resident, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, resident, st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
         } else {
-            int blocks = c->sm_count * 8;
-            auto kern = c->counting ? k_trace<IO, true, PTB_TRACE_BLK, false> : k_trace<IO, false, PTB_TRACE_BLK, false>;
-            kern<<<blocks, PTB_TRACE_BLK, TraceSmem<K, PTB_TRACE_BLK>::fixed, st>>>(S, io, cursor, count_ptr, c->d_specialq, sp_count, ctr);
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false> : k_trace_tree<IO, false, PTB_TRACE_BLK, false>;
+            kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK>::fixed, st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
         }
-        // rays set aside by the production kernel (axis-parallel / non-finite): exact-test kernel over the (usually empty) list;
-        // the list is reset for the next launch
-        ListedIO<IO> lio{io, c->d_specialq};
-        if (c->counting) k_trace_simple<ListedIO<IO>, 1, true><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
-        else k_trace_simple<ListedIO<IO>, 1, false><<<c->sm_count, PTB_TRACE_BLK, 0, st>>>(S, lio, sp_cursor, sp_count, ctr);
-        k_ctrl_special<<<1, 1, 0, st>>>(c->d_ctrl);
-        c->launches += 2;
+        c->launches++;
     }
     c->launches++;
 }
-// the production policy reads a provisional-hit record when the scene has an always-test list
-static bool use_pre(const TraceScene& S, int policy) { return policy == PTB_TRAVERSE_ORDERED && S.n >= 2 && S.nlist > 0; }
 static void launch_extend(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
-    if (use_pre(S, policy)) launch_trace_io(c, S, ExtendIO<true>{q.o, q.d, c->d_pre, c->st.hit}, policy, cursor, count_ptr);
-    else launch_trace_io(c, S, ExtendIO<false>{q.o, q.d, nullptr, c->st.hit}, policy, cursor, count_ptr);
+    launch_trace_io(c, S, ExtendIO{q.o, q.d, c->st.hit}, policy, 0, cursor, count_ptr);
 }
 static void launch_shadow(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
-    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, cursor, count_ptr);
+    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, 1, cursor, count_ptr);
 }
 
 void ptb_stage_begin(ptb_ctx* c, int stage) {
@@ -601,9 +588,8 @@ int ptb_stage_collect(ptb_ctx* c) {
 int ptb_wf_init(ptb_ctx* c) {
     int64_t np = c->max_paths;
     float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result,
-                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->d_pre};
+                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->tq.e[0], &c->tq.e[1], &c->tq.e[2], &c->tq.e[3], &c->tq.e[4]};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
-    PTB_CUDA(cudaMalloc(&c->d_specialq, sizeof(int) * np));
     PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
     PTB_CUDA(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
     PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
@@ -612,9 +598,9 @@ int ptb_wf_init(ptb_ctx* c) {
     int occ = 0;
     PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO<false>, 1, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO<false>, 0, false>, PTB_TRACE_BLK, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
     c->blocks_ref = c->sm_count * (occ > 0 ? occ : 4);
     c->blocks_generic = c->sm_count * 8;
     return 0;
@@ -775,9 +761,8 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
     c->launches += 2;
     int eff = ptb_effective_policy(c, policy);
     int* cur = &c->d_ctrl->pad[1]; const int* cnt = &c->d_ctrl->pad[0];
-    if (anyhit) launch_trace_io(c, S, TapIO<true, false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
-    else if (use_pre(S, eff)) launch_trace_io(c, S, TapIO<false, true>{c->sq.o, c->sq.d, c->d_pre, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
-    else launch_trace_io(c, S, TapIO<false, false>{c->sq.o, c->sq.d, nullptr, hit_dev, depth_dev, index_dev, uv_dev}, eff, cur, cnt);
+    if (anyhit) launch_trace_io(c, S, TapIO<true>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt);
+    else launch_trace_io(c, S, TapIO<false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt);
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
