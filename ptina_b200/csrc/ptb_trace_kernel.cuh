@@ -25,6 +25,9 @@
 
 #define PTB_TRACE_BLK 128
 #define PTB_TILE 16                 /* ray records per staged tile */
+#ifndef PTB_POOL
+#define PTB_POOL 64                 /* queue positions a warp reserves per atomic */
+#endif
 #ifndef PTB_FETCH_MIN
 #define PTB_FETCH_MIN 8             /* idle lanes that trigger a refill from the staged tile */
 #endif
@@ -152,10 +155,11 @@ template <class IO, bool COUNT>
 __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const int* count_ptr, ExpQ xq, int* tree_count, DevCounters* ctr) {
     constexpr bool ANYHIT = IO::kAnyHit;
     const int count = *count_ptr;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
     unsigned long long nrays = 0;
-    const int rounded = (count + 31) & ~31;
+    __shared__ int s_warp[8], s_base;
+    const int rounded = (count + 255) & ~255;          // every thread of a block runs the same number of iterations
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < rounded; idx += gridDim.x * 256) {
         bool live = false;
         RayIn in; in.item = -1; in.ro = v3s(0.0f); in.rd = v3s(0.0f); in.avoid_slot = -1; in.tmax = 0.0f; in.c = v3s(0.0f);
@@ -207,13 +211,21 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                 }
             }
         }
-        // append the survivors to the tree queue: one atomic per warp, contiguous records
+        // append the survivors to the tree queue: one atomic per block (every launch hammers the same counter), contiguous records
         const unsigned m = __ballot_sync(0xffffffffu, live);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(tree_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(tree_count, tot) : 0;
+        }
+        __syncthreads();
+        const int wbase = s_base + s_warp[warp];
+        __syncthreads();
         if (live) {
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            const int pos = wbase + __popc(m & ((1u << lane) - 1u));
             xq.e[0][pos] = make_float4(in.ro.x, in.ro.y, in.ro.z, __int_as_float(in.item));
             xq.e[1][pos] = make_float4(in.rd.x, in.rd.y, in.rd.z, __int_as_float(in.avoid_slot));
             xq.e[2][pos] = make_float4(R.r.x, R.r.y, R.r.z, delta);
@@ -287,10 +299,16 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     int tile_n0 = 0, tile_n1 = 0;              // number of valid records per buffer
     int cur_buf = 0, tile_pos = 0;             // consumption cursor in the current buffer
     bool tile_ready = false, exhausted = false;
+    int pool_next = 0, pool_end = 0;           // queue positions reserved by this warp (PTB_POOL per atomic on the shared cursor)
     auto fill = [&](int b) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, PTB_TILE);
-        base = __shfl_sync(FULL, base, 0);
+        if (pool_next >= pool_end) {
+            int p = 0;
+            if (lane == 0) p = atomicAdd(cursor, PTB_POOL);
+            p = __shfl_sync(FULL, p, 0);
+            pool_next = p; pool_end = p + PTB_POOL;
+        }
+        const int base = pool_next;
+        pool_next += PTB_TILE;
         const int nv = max(0, min(PTB_TILE, count - base));
 #pragma unroll
         for (int e = lane; e < K * PTB_TILE; e += 32) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
             // ---- idle lanes store their result and take the next staged records ----------------------------------------------------------
             if (!tile_ready) { cp_async_wait<1>(); __syncwarp(); tile_ready = true; }     // the older of the two groups in flight has landed
             const int nv = cur_buf == 0 ? tile_n0 : tile_n1;
-            if (nv == 0) exhausted = true;                                                 // tiles are handed out in order: nothing is left
+            if (nv == 0) exhausted = true;                                                 // positions are handed out in order: nothing is left
             const bool me = (idle >> lane) & 1u;
             if (me && item >= 0) { io.store(item, ret, contrib); item = -1; }
             const int k = tile_pos + __popc(idle & lt_mask);
