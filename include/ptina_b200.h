@@ -57,6 +57,8 @@ typedef struct ptb_tree_info {
     int32_t depth;        /* height of the tree in nodes, root = 1 (0 if !valid) */
     int32_t policy;       /* traversal policy in effect (PTB_TRAVERSE_REFERENCE / _ORDERED) */
     float build_ms;       /* device time of the whole build */
+    int32_t list_n;       /* triangles on the always-test list of the production traversal (big or ill-conditioned) */
+    int32_t list_overflow;/* 1 = more ill-conditioned triangles than the list holds: the production traversal is not used */
 } ptb_tree_info;
 
 typedef struct ptb_counters {

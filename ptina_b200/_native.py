@@ -29,7 +29,7 @@ class Caps(ctypes.Structure):
 
 class TreeInfo(ctypes.Structure):
     _fields_ = [('n', ctypes.c_int32), ('aabb_sweeps', ctypes.c_int32), ('valid', ctypes.c_int32), ('depth', ctypes.c_int32),
-                ('policy', ctypes.c_int32), ('build_ms', ctypes.c_float)]
+                ('policy', ctypes.c_int32), ('build_ms', ctypes.c_float), ('list_n', ctypes.c_int32), ('list_overflow', ctypes.c_int32)]
 
 
 class Counters(ctypes.Structure):

@@ -5,6 +5,7 @@
 //   genAABBs (lbvh.py:251-294, level-synchronous sweeps; min/max are exact so the boxes are identical).
 // Then: validation (every node one parent, leaf slots in order, height) and packing into the 64-byte node /
 // triangle records the traversal kernels read (ptb_traverse.cuh).
+#include <cstring>
 #include <cub/cub.cuh>
 #include "ptb_internal.h"
 
@@ -211,8 +212,9 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
 // point outside the triangle (derivation in DESIGN.md "Leaf boxes"):
 //   eps_T = 256u * cond * (|u| + |v|) + 64u * (|v0|_inf + |u| + |v|),  cond = uu*vv / |D| = 1 / sin^2(angle(u, v)),  u = 2^-24
 // valid while cond * (36 + 20 * max(|u|/|v|, |v|/|u|)) <= 1e6.  Flags (w of tlo): 1 = NEVER (D == 0 or not finite: s, t are
-// inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> always-test list), 4 = BIG (bounds cover more
-// than 1/16 of the scene's box area: hurts every ancestor's box -> always-test list if there is room).
+// inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> the leaf is bounded by its GATE box instead, the
+// reference box of its parent, which any accepted triangle's ray must pass anyway), 4 = BIG (bounds cover more than 1/16 of the
+// scene's box area: hurts every ancestor's box -> always-test list if there is room).
 #define PTB_TF_NEVER 1
 #define PTB_TF_MUST 2
 #define PTB_TF_BIG 4
@@ -249,14 +251,13 @@ __global__ void __launch_bounds__(BLK) k_tri_prep(const float* __restrict__ vert
     tlo[s] = make_float4(__fadd_rd(lo.x, -eps), __fadd_rd(lo.y, -eps), __fadd_rd(lo.z, -eps), __int_as_float(flags));
     thi[s] = make_float4(__fadd_ru(hi.x, eps), __fadd_ru(hi.y, eps), __fadd_ru(hi.z, eps), 0.0f);
 }
-// always-test list, in slot order (one block): every MUST slot, then BIG slots while there is room.  scal[11] = entries,
-// scal[12] = 1 if the MUST slots alone overflow the list (the production traversal is then not used).
+// always-test list, in slot order (one block): BIG slots while there is room (the rest stay in the tree).  scal[11] = entries.
 __global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, int n, int cap, int* __restrict__ list, int* scal) {
     __shared__ int s_count, s_warp[32];
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    for (int pass = 0; pass < 2; pass++) {
-        const int want = pass == 0 ? PTB_TF_MUST : PTB_TF_BIG;
+    {
+        const int want = PTB_TF_BIG;
         for (int base = 0; base < n; base += 1024) {
             int s = base + threadIdx.x;
             int fl = s < n ? __float_as_int(tlo[s].w) : 0;
@@ -270,10 +271,7 @@ __global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, i
             int pos = s_count + before + __popc(m & ((1u << lane) - 1u));
             if (take && pos < cap) { list[pos] = s; float4 t = tlo[s]; t.w = __int_as_float(fl | PTB_TF_LISTED); tlo[s] = t; }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                if (pass == 0 && s_count + total > cap) scal[12] = 1;
-                s_count = min(cap, s_count + total);
-            }
+            if (threadIdx.x == 0) s_count = min(cap, s_count + total);
             __syncthreads();
         }
     }
@@ -283,20 +281,26 @@ __global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, i
 // of a node of level `stamp` belong to earlier levels): union of the inflated bounds of the unlisted leaves below the node.
 // Empty = (lo, hi) = (+1e30, -1e30).
 __global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ child, const int* __restrict__ ready, int n, int stamp,
+                                                    const float* __restrict__ bmin, const float* __restrict__ bmax,
                                                     const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* __restrict__ nlo, float4* __restrict__ nhi) {
     int i = blockIdx.x * BLK + threadIdx.x;
     if (i >= n - 1 || ready[i] != stamp) return;
     int2 ch = child[i];
     V3 lo = v3s(1e30f), hi = v3s(-1e30f);
+    int must = 0;          // an ill-conditioned leaf below: its depth obeys no bound, so nothing above it may be culled by distance
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         int c = k == 0 ? ch.x : ch.y;
         float4 a, b;
-        if (c < n) { a = tlo[c]; b = thi[c]; if (__float_as_int(a.w) & (PTB_TF_NEVER | PTB_TF_LISTED)) continue; }
-        else { a = nlo[c - n]; b = nhi[c - n]; }
+        if (c < n) {
+            a = tlo[c]; b = thi[c];
+            const int fl = __float_as_int(a.w);
+            if (fl & (PTB_TF_NEVER | PTB_TF_LISTED)) continue;
+            if (fl & PTB_TF_MUST) { must = 1; a = make_float4(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2], 0.0f); b = make_float4(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2], 0.0f); }
+        } else { a = nlo[c - n]; b = nhi[c - n]; must |= __float_as_int(a.w); }
         lo = vmin(lo, mk3(a.x, a.y, a.z)); hi = vmax(hi, mk3(b.x, b.y, b.z));
     }
-    nlo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f); nhi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    nlo[i] = make_float4(lo.x, lo.y, lo.z, __int_as_float(must)); nhi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
 }
 // packed 64-byte traversal node: both children's traversal boxes and ids (-1 = nothing below: listed / never-hit leaf or an
 // internal node with an empty box); per leaf slot: its gate (parent) and the gate's REFERENCE box (bmin/bmax of the parent).
@@ -315,13 +319,19 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const int2* __restrict__ chi
         if (c < 0 || c >= 2 * n - 1) id[k] = -1;
         else if (c < n) {
             lo[k] = tlo[c]; hi[k] = thi[c];
-            if (__float_as_int(lo[k].w) & (PTB_TF_NEVER | PTB_TF_LISTED)) id[k] = -1;
+            const int fl = __float_as_int(lo[k].w);
+            if (fl & (PTB_TF_NEVER | PTB_TF_LISTED)) id[k] = -1;
+            else if (fl & PTB_TF_MUST) {      // ill-conditioned: bounded by its gate box (this node's reference box), never culled by distance
+                lo[k] = make_float4(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2], 0.0f); hi[k] = make_float4(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2], 0.0f);
+                id[k] |= PTB_NODE_MUST;
+            }
             gate[c] = i;
             gbox[2 * c] = make_float4(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2], 0.0f);
             gbox[2 * c + 1] = make_float4(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2], 0.0f);
         } else {
             lo[k] = nlo[c - n]; hi[k] = nhi[c - n];
             if (lo[k].x > hi[k].x) id[k] = -1;
+            else if (__float_as_int(lo[k].w)) id[k] |= PTB_NODE_MUST;
         }
     }
     Node64 N;
@@ -415,7 +425,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
         // traversal structure: inflated leaf bounds, always-test list, pruned traversal boxes, packed nodes
         k_tri_prep<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, scal, c->d_tlo, c->d_thi);
         k_build_list<<<1, 1024, 0, st>>>(c->d_tlo, n, PTB_LIST_CAP, c->d_list, c->d_scalars);
-        for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
+        for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
         k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_bmin, c->d_bmax, n, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_nodes, c->d_gate, c->d_gbox);
         c->launches += 4 + sweeps;
     }
@@ -435,6 +445,8 @@ int ptb_lbvh_build(ptb_ctx* c) {
         PTB_CUDA(cudaStreamSynchronize(st));
         c->scene_abs = 0.0f;
         for (int k = 0; k < 6; k++) c->scene_abs = fmaxf(c->scene_abs, fabsf(h_root[k]));
+        c->root_must = 0;
+        if (h_troot[0] <= h_troot[4]) { int m; memcpy(&m, &h_troot[3], 4); c->root_must = m != 0; }
         if (h_troot[0] <= h_troot[4]) for (int k = 0; k < 3; k++) c->scene_abs = fmaxf(c->scene_abs, fmaxf(fabsf(h_troot[k]), fabsf(h_troot[4 + k])));
         valid = (n > 1) && h_scal[9] == 0;
         depth = valid ? h_scal[10] : 0;
@@ -450,6 +462,8 @@ int ptb_lbvh_build(ptb_ctx* c) {
     c->tree_info.valid = valid;
     c->tree_info.depth = depth;
     c->tree_info.build_ms = ms;
+    c->tree_info.list_n = c->list_n;
+    c->tree_info.list_overflow = c->list_overflow;
     c->tree_info.policy = ptb_effective_policy(c, c->traversal_request);
     return 0;
 }

@@ -98,6 +98,7 @@ struct ptb_ctx {
     float4 *d_nlo = nullptr, *d_nhi = nullptr;   // [n-1] per internal node: traversal box (union of the unlisted leaves below)
     int32_t* d_list = nullptr;      // always-test list (leaf slots), PTB_LIST_CAP entries
     int list_n = 0, list_overflow = 0;
+    int root_must = 0;
     float scene_abs = 0.0f;         // largest absolute coordinate of the reference root box and the traversal root box
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
     int32_t* d_scalars = nullptr;   // small device scratch (bounds as ordered ints, flags)

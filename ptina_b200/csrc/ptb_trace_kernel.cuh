@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                     if (COUNT) C.boxes++;
                     delta = trav_delta(in.ro, S.scene_abs);
                     const RayTrav Q = ray_trav(R, delta);
-                    live = S.nlo[0].x <= S.nhi[0].x && slab_trav(S.nlo[0], S.nhi[0], R, Q, &lb) && !(lb > best + best * PTB_CULL_GUARD);
+                    live = S.nlo[0].x <= S.nhi[0].x && slab_trav(S.nlo[0], S.nhi[0], R, Q, &lb) && (S.root_must || !(lb > best + best * PTB_CULL_GUARD));
                 }
                 if (!live) {
                     if (ret.hit) ret.index = S.leaf[ret.slot];
@@ -395,10 +395,14 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     if (SMEM) { N.a = s_node[cur]; N.b = s_node[(n - 1) + cur]; N.c = s_node[2 * (n - 1) + cur]; N.d = s_node[3 * (n - 1) + cur]; }
                     else N = S.nodes[cur];
                     if (COUNT) { C.nodes++; C.boxes += 2; }
-                    const int c0 = __float_as_int(N.a.w), c1 = __float_as_int(N.b.w);      // -1: nothing below
+                    const int w0 = __float_as_int(N.a.w), w1 = __float_as_int(N.b.w);      // -1: nothing below
+                    const int c0 = w0 & PTB_NODE_ID, c1 = w1 & PTB_NODE_ID;
+                    const bool must0 = (w0 & PTB_NODE_MUST) != 0, must1 = (w1 & PTB_NODE_MUST) != 0;
                     float n0, n1;
-                    const bool h0 = slab_trav(N.a, N.b, R, Q, &n0) && !(n0 > cull) && c0 >= 0;
-                    const bool h1 = slab_trav(N.c, N.d, R, Q, &n1) && !(n1 > cull) && c1 >= 0;
+                    bool h0 = slab_trav(N.a, N.b, R, Q, &n0) && w0 >= 0, h1 = slab_trav(N.c, N.d, R, Q, &n1) && w1 >= 0;
+                    if (must0) n0 = 0.0f;               // an ill-conditioned triangle below: no distance bound holds
+                    if (must1) n1 = 0.0f;
+                    h0 = h0 && !(n0 > cull); h1 = h1 && !(n1 > cull);
                     const bool leaf0 = c0 < n, leaf1 = c1 < n;
                     const bool p0 = h0 && leaf0 && c0 != avoid_slot, p1 = h1 && leaf1 && c1 != avoid_slot;
                     if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c0; s_qnear[k][threadIdx.x] = n0; q_count++; }

@@ -20,6 +20,10 @@
 // child id < n : leaf slot (box = that triangle's bounds; unused by the predicates -- the reference does not box-test
 // leaves);  id >= n : internal node id-n.
 struct __align__(16) Node64 { float4 a, b, c, d; };
+// traversal nodes (lbvh.cu k_pack_nodes): child id -1 = nothing below; PTB_NODE_MUST set = an ill-conditioned triangle below,
+// whose computed depth obeys no bound: the child is never culled by distance
+#define PTB_NODE_MUST 0x40000000
+#define PTB_NODE_ID 0x3FFFFFFF
 // 64-byte packed triangle, indexed by sorted leaf slot:
 //   a = (v0.xyz, 1/D)  b = (u.xyz, uu)  c = (v.xyz, uv)  d = (n.xyz, vv)     u=v1-v0, v=v2-v0, n=u x v, D = uv*uv - uu*vv
 // Every field is the f32 expression geometries.py:121-141 evaluates per test (they depend on the triangle only), so
@@ -36,6 +40,7 @@ struct TraceScene {
     const float4* __restrict__ nlo;      // [n-1] traversal boxes of the internal nodes (lo, hi); [0] = the root's
     const float4* __restrict__ nhi;
     float scene_abs;                     // largest absolute coordinate of the (inflated) scene bounds
+    int root_must;                       // the traversal root has an ill-conditioned triangle below it (no distance cull)
     const int* __restrict__ list;        // always-test list (leaf slots): big or ill-conditioned triangles kept out of the traversal tree
     int nlist;
     // reference arrays (lbvh.py:50-59) for the literal traversal
@@ -305,9 +310,10 @@ PTB_D HitRec trace_reference(const TraceScene& S, V3 ro, V3 rd, int avoid, Trace
 }
 
 // ---- ordered traversal with the EXACT predicates, over the reference's own arrays (child / bmin / bmax) ----------------------
-// Near child first; sub-trees whose exact entry distance is beyond the current best (plus a relative guard band: the compare mixes
-// a box distance with a triangle distance, which are rounded differently) are skipped; ties in depth go to the larger leaf slot.
-// The checker for the production kernel (PTB_TRAVERSE_ORDERED_EXACT) and the tracer of the rays it sets aside.
+// Near child first; ties in depth go to the larger leaf slot.  No distance culling: the f32 depth of a triangle is not bounded by
+// the f32 entry distance of the reference boxes around it (grazing rays / sliver triangles), so only the reference's own hit / miss
+// gating is used -- every triangle the reference tests is tested.  The checker for the production kernel
+// (PTB_TRAVERSE_ORDERED_EXACT) and the tracer of the rays it sets aside (axis-parallel, non-finite).
 // ANYHIT: stop at the first accepted triangle with depth <= tmax (shadow rays: the reference calls the ray occluded
 // iff its CLOSEST hit has depth <= dis, which holds iff ANY reachable triangle has one).
 template <bool ANYHIT, bool COUNT>
@@ -325,7 +331,7 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
     if (!slab_fast(S.bmin[0], S.bmin[1], S.bmin[2], S.bmax[0], S.bmax[1], S.bmax[2], P, &nr)) return ret;
     const int avoid_slot = avoid >= 0 ? S.slot_of[avoid] : -1;
     float best = ANYHIT ? fminf(tmax, PTB_INF) : PTB_INF;
-    float cull = best + best * PTB_CULL_GUARD;
+    const float cull = PTB_INF * 4.0f;        // nothing is culled by distance
     int stack_id[PTB_STACK];
     float stack_near[PTB_STACK];
     int sp = 0;
@@ -334,7 +340,6 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
     while (true) {
         int pend0 = -1, pend1 = -1;
         while (cur >= 0) {
-            if (cur_near > cull) { cur = -1; break; }
             const int2 ch = S.child[cur];
             if (COUNT) C->nodes++;
             const int c0 = ch.x, c1 = ch.y;
@@ -367,16 +372,14 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
                     if (dep < PTB_INF) { ret.hit = 1; ret.depth = dep; ret.u = s; ret.v = t; ret.slot = slot; ret.index = S.leaf[slot]; return ret; }
                 } else if (dep < ret.depth || (ret.hit && slot > ret.slot)) {     // here dep <= best == ret.depth
                     ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
-                    best = dep; cull = dep + dep * PTB_CULL_GUARD;
+                    best = dep;
                 }
             }
         }
         if (cur < 0) {
-            while (sp > 0) {
-                --sp;
-                if (!(stack_near[sp] > cull)) { cur = stack_id[sp]; cur_near = stack_near[sp]; break; }
-            }
-            if (cur < 0) break;
+            if (sp == 0) break;
+            --sp;
+            cur = stack_id[sp]; cur_near = stack_near[sp];
         }
     }
     if (!ANYHIT && ret.hit) ret.index = S.leaf[ret.slot];

@@ -41,6 +41,7 @@ def test_lbvh_bit_exact(gpu, name):
     for key in ('bmin', 'bmax'):
         assert np.array_equal(bits(a[key]), bits(b[key])), f'{name}: {key} differs'
     assert info.valid == 1 and info.depth == o.validate_tree() and info.policy == _native.TRAVERSE_ORDERED
+    assert info.list_overflow == 0 and info.list_n == {'cornell_boxes': 18, 'cornell_monkey': 10}.get(name, info.list_n)
 
 
 @pytest.mark.parametrize('name', list(SMALL))
@@ -165,6 +166,87 @@ def test_adversarial_rays_match_reference_order(gpu, name):
         want = (h & (ref['depth'] <= dis)).astype(np.int32)
     for policy in (_native.TRAVERSE_ORDERED, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
         assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want), f'policy {policy}: shadow queries differ'
+
+
+def _soup(rng, kind):
+    """Triangle soups that stress the production traversal's conservative machinery: needle / sliver triangles (ill-conditioned
+    Face.intersect arithmetic -> bounded by their gate box), exactly degenerate ones (never hit), triangles spanning the whole scene
+    (always-test list, and its overflow), tiny ones far from the origin (large absolute rounding), duplicates (depth ties)."""
+    tris = []
+    def add(v0, e1, e2):
+        tris.append(np.stack([v0, v0 + e1, v0 + e2], 1))
+    m = 700
+    c = rng.uniform(-1, 1, (m, 3)); add(c, rng.normal(size=(m, 3)) * 0.08, rng.normal(size=(m, 3)) * 0.08)            # ordinary
+    c = rng.uniform(-1, 1, (150, 3)); e = rng.normal(size=(150, 3)) * 0.3
+    add(c, e, e * rng.uniform(0.2, 1.5, (150, 1)) + rng.normal(size=(150, 3)) * 10.0 ** rng.uniform(-7, -2, (150, 1)))        # slivers
+    c = rng.uniform(-1, 1, (40, 3)); e = rng.normal(size=(40, 3)) * 0.2
+    add(c, e, e * 2.0); add(c, e, e * 0.0)                                                                        # degenerate
+    c = rng.uniform(-1, 1, (60, 3)) * 0.7 + 6.0; add(c, rng.normal(size=(60, 3)) * 1e-3, rng.normal(size=(60, 3)) * 1e-3)   # tiny, off-centre
+    nbig = {'few_big': 6, 'many_big': 50, 'no_big': 0}[kind]
+    if nbig:
+        c = rng.uniform(-1.2, -0.8, (nbig, 3)); add(c, rng.uniform(1.5, 2.5, (nbig, 3)), rng.uniform(1.5, 2.5, (nbig, 3)) * [1, -1, 1])
+    t = np.concatenate(tris, 0).astype(np.float32)
+    t = np.concatenate([t, t[:12]], 0)                                                                            # exact duplicates
+    n = t.shape[0]
+    nrm = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]); nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    v = np.zeros((n, 3, 8), np.float32); v[:, :, :3] = t; v[:, :, 3:6] = nrm[:, None, :]
+    return v.reshape(n * 3, 8)
+
+
+@pytest.mark.parametrize('kind', ['few_big', 'many_big', 'no_big'])
+def test_triangle_soup_matches_reference_order(gpu, kind):
+    from ptina_b200.model import ModelPool
+    from ptina_b200.tree import BVHTree
+    for seed in range(40):       # Morton-code runs of >= 3 make the reference's hierarchy a non-tree (it raises): take the first proper one
+        rng = np.random.default_rng(1000 * seed + {'few_big': 5, 'many_big': 6, 'no_big': 7}[kind])
+        verts = _soup(rng, kind)
+        nf = verts.shape[0] // 3
+        ModelPool().load(verts, np.zeros(nf, np.int32))
+        try:
+            BVHTree().build()
+        except RuntimeError:
+            continue
+        if gpu.tree.valid:
+            break
+    o = oracle.Oracle(); o.load_model(verts, np.zeros(nf, np.int32)); o.build_tree()
+    info = gpu.tree
+    assert info.valid == 1 and info.policy == _native.TRAVERSE_ORDERED, 'no proper tree found: the production traversal was not exercised'
+    a, b = gpu.export_tree(), o.export_tree()
+    for key in ('mc', 'id', 'leaf', 'child'):
+        assert np.array_equal(a[key], b[key])
+    assert info.list_n == {'few_big': 6, 'many_big': 32, 'no_big': 0}[kind] and info.list_overflow == 0
+    tri = verts[:, :3].reshape(nf, 3, 3)
+    m = 30000
+    f = rng.integers(0, nf, m)
+    w = rng.dirichlet([1, 1, 1], m).astype(np.float32)
+    # targets: interior points, exact vertices, exact edge midpoints, points just outside an edge
+    tgt = (tri[f] * w[:, :, None]).sum(1)
+    sel = rng.integers(0, 4, m)
+    k = rng.integers(0, 3, m)
+    tgt = np.where((sel == 1)[:, None], tri[f, k], tgt)
+    mid = (tri[f, k] + tri[f, (k + 1) % 3]) * np.float32(0.5)
+    tgt = np.where((sel == 2)[:, None], mid, tgt)
+    out = mid + (mid - tri[f, (k + 2) % 3]) * (10.0 ** rng.uniform(-7, -3, (m, 1))).astype(np.float32)
+    tgt = np.where((sel == 3)[:, None], out, tgt).astype(np.float32)
+    org = rng.uniform(-3, 3, (m, 3)).astype(np.float32)
+    org[: m // 4] = (tri[rng.integers(0, nf, m // 4)] * rng.dirichlet([1, 1, 1], m // 4).astype(np.float32)[:, :, None]).sum(1)    # origins on surfaces
+    d = tgt - org; d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+    d[m // 2: m // 2 + 2000, rng.integers(0, 3)] *= np.float32(1e-4)                                                 # nearly axis-parallel
+    rays = np.ascontiguousarray(np.concatenate([org, d], 1), np.float32)
+    avoid = np.where(rng.random(m) < 0.3, f, -1).astype(np.int32)
+    ref = o.intersect(rays, avoid)
+    h = ref['hit'] == 1
+    assert h.mean() > 0.3
+    policies = (_native.TRAVERSE_AUTO, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE)
+    for policy in policies:
+        got = gpu.intersect(rays, avoid, policy)
+        bad = np.nonzero(got['index'] != ref['index'])[0]
+        assert bad.size == 0, f'{kind} policy {policy}: {bad.size} ids differ, first ray {rays[bad[0]]} got {got["index"][bad[0]]} want {ref["index"][bad[0]]}'
+        assert np.array_equal(bits(got['depth'])[h], bits(ref['depth'])[h]) and np.array_equal(bits(got['uv'])[h], bits(ref['uv'])[h])
+    dis = np.where(h, ref['depth'] * rng.choice([0.5, 1.0, 1.0, 1.5], m), 5.0).astype(np.float32)
+    want = (h & (ref['depth'] <= dis)).astype(np.int32)
+    for policy in policies:
+        assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want), f'{kind} policy {policy}: shadow queries differ'
 
 
 def _random_materials(rng, m):
