@@ -234,6 +234,7 @@ def run_gpu(args):
         print('e2e per-step wall ms:', [round(x, 2) for x in dbg], {k: v[-args.steps:] for k, v in e2e_parts.items()}, file=sys.stderr)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    e2e_steps_ms = [round(x, 3) for x in dbg]
     t = torch.tensor([e2e_ms], device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -248,9 +249,14 @@ def run_gpu(args):
             pass
         hbm_peak, peak_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json)') if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md)')
         l2_gbs = ctx.measure_l2(64, 20)
-        # dominant kernel = extend (+ shadow, same traversal code): algorithmic bytes per launch = 64 B per node visit +
-        # 64 B per triangle test + 48 B per ray (32 B ray in, 16 B hit out)  -- DESIGN.md "Roofline"
+        # dominant stage = BVH traversal (extend + shadow; each stage launch = k_trace_pre + k_trace_tree): algorithmic bytes per
+        # launch = 64 B per node visit + 64 B per triangle test + 48 B per ray (32 B ray in, 16 B hit out)  -- DESIGN.md "Roofline"
         n_trav_launches = 5 * args.steps * (2 if eng == _native.ENGINE_PATH else 1)
+        ncu = {}
+        try:    # DRAM bytes / issue-slot utilisation of the traversal kernels from the committed ncu capture of this build
+            ncu = json.load(open(os.path.join(ROOT, 'profiles', 'traversal_ncu.json'))).get(sc['name'], {})
+        except Exception:
+            pass
         trav_ms = stage['extend'] + stage['shadow']
         alg_bytes_step = 64.0 * cnt['node_visits'] + 64.0 * cnt['tri_tests'] + 48.0 * cnt['rays']
         achieved = alg_bytes_step * args.steps / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
@@ -260,14 +266,15 @@ def run_gpu(args):
                 'spp_per_s': spp * world * args.steps / (ms * 1e-3),
                 'rays_per_step': total_rays_per_step,
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(verts_pin.numel() * 4 + mtl_pin.numel() * 4),
-                        'd2h_bytes_per_step': int(img_pin.numel() * 4), 'ms_per_step': e2e_ms / args.steps,
+                        'd2h_bytes_per_step': int(img_pin.numel() * 4), 'ms_per_step': e2e_ms / args.steps, 'ms_steps': e2e_steps_ms,
                         'path': 'ModelPool.load(pinned host) + BVHTree.build + FilmTable.clear + PathEngine.render_range + FilmTable.get_image(host)'},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': (achieved / hbm_peak) if achieved else None, 'traffic': None,
-                             'kernel': 'k_extend + k_shadow (BVH traversal)', 'launches': n_trav_launches, 'avg_launch_ms': trav_ms / n_trav_launches,
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': (achieved / hbm_peak) if achieved else None, 'traffic': ncu.get('dram_bytes_per_launch'),
+                             'kernel': 'k_trace_pre + k_trace_tree (BVH traversal: extend and shadow stages)', 'ncu': ncu or None, 'launches': n_trav_launches, 'avg_launch_ms': trav_ms / n_trav_launches,
                              'algorithmic_bytes_per_launch': alg_bytes_step * args.steps / n_trav_launches, 'peak_source': peak_src,
                              'l2_peak_gbs_measured': l2_gbs, 'frac_of_l2': (achieved / l2_gbs) if achieved else None,
-                             'note': 'gather workload served from L1/L2 (scene is cache resident): HBM is the schema bound, the L2 figure is the physical one'},
+                             'note': 'gather workload served from shared memory / L1 / L2 (the scene is cache resident): HBM is the schema bound; '
+                                     'what binds is instruction issue (ncu: issue-slot utilisation, lanes per instruction -- profiles/)'},
                 'stage_ms_per_step': {k: v / args.steps for k, v in stage.items()},
                 'counters_per_step_rank0': cnt,
                 'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms},

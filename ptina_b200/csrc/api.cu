@@ -137,7 +137,7 @@ int ptb_destroy(ptb_ctx* c) {
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
                     c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
                     c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->tq.e[0], c->tq.e[1], c->tq.e[2], c->tq.e[3], c->tq.e[4],
-                    c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold};
+                    c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold, c->d_resolve};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -358,10 +358,18 @@ static int resolve_common(ptb_ctx* c, int pass, int mode, float* out, int memspa
     CHECK_CTX(c);
     DeviceGuard g(c->device);
     if (pass < 0 || pass >= c->caps.max_filmpasses) { ptb_set_error("film pass %d out of range", pass); return 1; }
-    Out<float> o;
-    if (o.set(out, count, memspace)) return 1;
-    if (ptb_wf_resolve(c, pass, mode, o.dev)) return 1;
-    return o.finish(c);
+    if (memspace == PTB_DEVICE) return ptb_wf_resolve(c, pass, mode, out);
+    // host destination: resolve into a context-owned staging buffer (grow-only: no cudaMalloc / cudaFree on the per-frame path)
+    if (count > c->resolve_cap) {
+        if (c->d_resolve) cudaFree(c->d_resolve);
+        c->d_resolve = nullptr; c->resolve_cap = 0;
+        PTB_CUDA(cudaMalloc((void**)&c->d_resolve, sizeof(float) * count));
+        c->resolve_cap = count;
+    }
+    if (ptb_wf_resolve(c, pass, mode, c->d_resolve)) return 1;
+    PTB_CUDA(cudaMemcpyAsync(out, c->d_resolve, sizeof(float) * count, cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 int ptb_get_image(ptb_ctx* c, int pass, float* out, int memspace) { return resolve_common(c, pass, 0, out, memspace, c ? (size_t)c->nx * c->ny * 4 : 0); }
 int ptb_fast_export_image(ptb_ctx* c, int pass, float* out, int memspace) { return resolve_common(c, pass, 1, out, memspace, c ? (size_t)c->nx * c->ny * 3 : 0); }

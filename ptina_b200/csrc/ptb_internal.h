@@ -109,6 +109,7 @@ struct ptb_ctx {
     // ---- film (filmtable.py:12-14) ----
     int nx = 0, ny = 0;
     float4* d_film = nullptr;       // [passes][max_filmsize]
+    float* d_resolve = nullptr; size_t resolve_cap = 0;   // staging for host-side get_image / fast_export_image
 
     // ---- wavefront ----
     int64_t max_paths = 0;
