@@ -243,6 +243,16 @@ PTB_D void cp_async16(void* smem_dst, const void* gmem_src) {
 }
 PTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// 64-byte record through two 256-bit loads (sm_100: LDG.E.256): half the L1 wavefronts of four 128-bit loads when every lane of a
+// warp reads a different record
+PTB_D Node64 ld_node256(const Node64* p) {
+    Node64 N;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(N.a.x), "=f"(N.a.y), "=f"(N.a.z), "=f"(N.a.w), "=f"(N.b.x), "=f"(N.b.y), "=f"(N.b.z), "=f"(N.b.w) : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(N.c.x), "=f"(N.c.y), "=f"(N.c.z), "=f"(N.c.w), "=f"(N.d.x), "=f"(N.d.y), "=f"(N.d.z), "=f"(N.d.w) : "l"(reinterpret_cast<const char*>(p) + 32));
+    return N;
+}
 
 #define PTB_PQ 4                    /* pending-leaf ring entries per lane */
 #ifndef PTB_NODE_REPS
@@ -252,7 +262,7 @@ template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group 
 #define PTB_TRACE_BLK_S 768         /* threads of the shared-memory-resident variant (one CTA per SM) */
 #endif
 #ifndef PTB_TRACE_MINB
-#define PTB_TRACE_MINB 8            /* resident CTAs per SM the global-memory variant is compiled for */
+#define PTB_TRACE_MINB 6            /* resident CTAs per SM the global-memory variant is compiled for (80 registers, no spills) */
 #endif
 
 // dynamic shared memory layout of k_trace_tree (bytes), shared by the kernel and the host launch code
@@ -327,19 +337,21 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
-    // stack entries: low word = internal node, high word = lower bound of the depth of anything below it.  The top lives in `tos`
-    // (valid iff sp > 0; reloaded at pop time, consumed at the next pop), the entries below it in stack[1 .. sp-1].
-    unsigned long long stack[PTB_STACK + 1];
-    unsigned long long tos = 0;
+    // stack entries: low word = internal node, high word = lower bound of the depth of anything below it.  A pop is issued as soon
+    // as a lane runs out of children (end of its node step) into `pe`, and consumed at the start of its next node step, so the
+    // local-memory load has a whole iteration to land.
+    unsigned long long stack[PTB_STACK];
+    unsigned long long pe = 0;                 // popped entry, valid iff `popped`
+    bool popped = false;
     int sp = 0;
-    int cur = -1;                              // node to visit next, -1: take it from the stack
+    int cur = -1;                              // node to visit next; -1: none (take `pe` if popped)
     float cur_near = 0.0f;
     int q_head = 0, q_count = 0;
 
     while (true) {
         // a lane can take a node step if it has a node (current or stacked) and room for two more pending leaves; a leaf step if
         // a leaf is pending.  A lane with neither is idle: finished (result not stored yet) or never started.
-        const bool node_ok = (cur != -1 || sp > 0) && q_count <= PTB_PQ - 2;
+        const bool node_ok = (cur != -1 || popped) && q_count <= PTB_PQ - 2;
         const bool leaf_ok = q_count > 0;
         const unsigned mn = __ballot_sync(FULL, node_ok), ml = __ballot_sync(FULL, leaf_ok);
         const unsigned idle = ~(mn | ml);
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     best = ret.depth;
                 }
                 cull = best + best * PTB_CULL_GUARD;
-                sp = 0; cur_near = 0.0f; q_head = 0; q_count = 0;
+                sp = 0; popped = false; cur_near = 0.0f; q_head = 0; q_count = 0;
                 cur = 0;                // the root (its children's boxes are tested in its node step)
             }
             tile_pos = min(tile_pos + __popc(idle), nv);
@@ -383,17 +395,13 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
             // ---- node step: one 64-byte node, both children's slab tests ----------------------------------------------------------------------
 #pragma unroll 1
             for (int rep = 0; rep < PTB_NODE_REPS; rep++)
-            if (rep == 0 ? node_ok : ((cur != -1 || sp > 0) && q_count <= PTB_PQ - 2)) {
-                if (cur == -1) {                        // pop (the reload of `tos` is not consumed before the next pop)
-                    cur = (int)(unsigned)tos; cur_near = __int_as_float((int)(tos >> 32));
-                    --sp;
-                    tos = stack[sp];
-                }
+            if (rep == 0 ? node_ok : ((cur != -1 || popped) && q_count <= PTB_PQ - 2)) {
+                if (cur == -1) { cur = (int)(unsigned)pe; cur_near = __int_as_float((int)(pe >> 32)); popped = false; }
                 if (cur_near > cull) cur = -1;          // nothing below can beat the best hit found since it was pushed / chosen
                 else {
                     Node64 N;
                     if (SMEM) { N.a = s_node[cur]; N.b = s_node[(n - 1) + cur]; N.c = s_node[2 * (n - 1) + cur]; N.d = s_node[3 * (n - 1) + cur]; }
-                    else N = S.nodes[cur];
+                    else N = ld_node256(S.nodes + cur);
                     if (COUNT) { C.nodes++; C.boxes += 2; }
                     const int w0 = __float_as_int(N.a.w), w1 = __float_as_int(N.b.w);      // -1: nothing below
                     const int c0 = w0 & PTB_NODE_ID, c1 = w1 & PTB_NODE_ID;
@@ -410,15 +418,15 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     const bool d0 = h0 && !leaf0, d1 = h1 && !leaf1;
                     const bool first1 = !(n0 < n1);     // nearer first
                     if (d0 && d1) {
-                        stack[sp] = tos;                // slot 0 receives garbage when sp == 0 (never read back as an entry)
-                        tos = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
-                        sp++;                           // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
+                        // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
+                        stack[sp++] = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
                         if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
                         cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
                     } else if (d0) { cur = c0 - n; cur_near = n0; }
                     else if (d1) { cur = c1 - n; cur_near = n1; }
                     else cur = -1;
                 }
+                if (cur == -1 && sp > 0) { pe = stack[--sp]; popped = true; }      // out of children: issue the pop now
             }
         } else {
             // ---- leaf step: the oldest pending leaf of every lane that has one ---------------------------------------------------------------
@@ -426,20 +434,20 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                 const int slot = s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
                 q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
                 if (!(lnear > cull)) {
-                    // the reference tests this triangle only if its gate box passes Box.intersect: conservative test first
-                    const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
-                    float gl; bool gsure;
-                    if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure)) {
-                        const Tri64 T = S.tris[slot];
-                        if (COUNT) C.tris++;
-                        float dep, s, t;
-                        if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
-                            // here dep <= best.  `gsure`: the gate certainly passes; otherwise the ray grazes it: exact test
-                            const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
-                            if (better && (gsure || gate_passes(S, S.gate[slot], R.o, R.d))) {
+                    const Tri64 T = S.tris[slot];
+                    if (COUNT) C.tris++;
+                    float dep, s, t;
+                    if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {
+                        // here dep <= best.  The reference tests this triangle only if its gate box passes Box.intersect: conservative
+                        // test (certain pass / certain miss), exact test when the ray grazes the gate
+                        const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+                        if (better) {
+                            const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
+                            float gl; bool gsure;
+                            if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], R.o, R.d))) {
                                 ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
                                 ret.index = S.leaf[slot];                         // face id: only read when the ray is stored
-                                if (ANYHIT) { cur = -1; sp = 0; q_count = 0; }    // occluded: done (stored when the lane is refilled)
+                                if (ANYHIT) { cur = -1; sp = 0; popped = false; q_count = 0; }    // occluded: done (stored when the lane is refilled)
                                 else { best = dep; cull = dep + dep * PTB_CULL_GUARD; }
                             }
                         }
