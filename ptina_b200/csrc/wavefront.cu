@@ -52,6 +52,25 @@ struct Rng {
         return __ldg(&tab[pymod(i, dim)]);
     }
 };
+// k consecutive draws starting at draw c0: one modulo, then increments with wrap-around (identical indices; the i32 wrap of
+// `self.i += 1` inside the run falls back to the per-draw modulo)
+struct RngRun {
+    const Rng& g; int i0, b0; bool fast;
+    PTB_D RngRun(const Rng& g_, int c0) : g(g_), i0(0), b0(0), fast(false) {
+        if (g.dim != 0) {
+            i0 = (int)((unsigned)g.base + (unsigned)c0);
+            fast = i0 <= 0x7fffffff - 16;
+            b0 = pymod(i0, g.dim);
+        } else i0 = c0;
+    }
+    PTB_D float draw(int j) const {     // j-th draw of the run, j < 16
+        if (g.dim == 0) return g.tab[i0 + j];
+        int b;
+        if (fast) { b = b0 + j; if (b >= g.dim) b -= g.dim; }
+        else b = pymod((int)((unsigned)i0 + (unsigned)j), g.dim);
+        return __ldg(&g.tab[b]);
+    }
+};
 
 // ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
 // returns the queue position reserved for this thread (-1 if !flag)
@@ -199,10 +218,11 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                 if (sign < 0.0f) normal = -normal;
                 V3 wi = -rd;
                 int c0;
+                const RngRun run(rng, ENGINE == PTB_ENGINE_PATH ? 2 + 6 * (depth - 1) : 2 + 3 * (depth - 1));
                 if (ENGINE == PTB_ENGINE_PATH) {
-                    c0 = 2 + 6 * (depth - 1);
+                    c0 = 0;
                     // path.py:48-56 next-event estimation
-                    V3 ls = mk3(rng.draw(c0), rng.draw(c0 + 1), rng.draw(c0 + 2));
+                    V3 ls = mk3(run.draw(c0), run.draw(c0 + 1), run.draw(c0 + 2));
                     LitSample li = light_sample(P, hitpos, ls);
                     if (any_gt(li.color, 0.0f)) {
                         V3 brdf_clr = disney_brdf(mat, normal, sign, wi, li.dir);
@@ -219,10 +239,10 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                     }
                     c0 += 3;
                 } else {
-                    c0 = 2 + 3 * (depth - 1);
+                    c0 = 0;
                 }
                 // path.py:58-62 / brute.py:56-60
-                BSDFSample bs = disney_bounce(mat, normal, sign, wi, mk3(rng.draw(c0), rng.draw(c0 + 1), rng.draw(c0 + 2)));
+                BSDFSample bs = disney_bounce(mat, normal, sign, wi, mk3(run.draw(c0), run.draw(c0 + 1), run.draw(c0 + 2)));
                 thr = thr * bs.color;
                 last_pdf = bs.pdf;                                         // path.py:61
                 st.thr[p] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));

@@ -20,6 +20,19 @@ def _expand_factor(fac):
     return fac + [1.0] if len(fac) == 3 else fac
 
 
+def pack_materials(materials, fac=None, tex=None):
+    """MaterialPool.load's table fill (mtllib.py:58-77) as a host function: each material's list is zipped with the 12 slots;
+    slots a short list does not mention keep what the table held (zero-initialised: factor 0, texture id 0)."""
+    materials = list(materials)
+    if fac is None:
+        fac, tex = np.zeros((len(materials), 12, 4), np.float32), np.zeros((len(materials), 12), np.int32)
+    for i, material in enumerate(materials):
+        for slot, (f, t) in zip(range(12), material):
+            fac[i, slot] = _expand_factor(f)
+            tex[i, slot] = t
+    return fac, tex
+
+
 class MaterialPool(metaclass=Singleton):
     def __init__(self, count=2**6):
         self.capacity = count
@@ -31,9 +44,6 @@ class MaterialPool(metaclass=Singleton):
     def load(self, materials):
         materials = list(materials)
         assert len(materials) <= self.capacity, 'too many materials'
-        for i, material in enumerate(materials):
-            for slot, (fac, tex) in zip(range(12), material):
-                self.fac[i, slot] = _expand_factor(fac)
-                self.tex[i, slot] = tex
+        pack_materials(materials, self.fac, self.tex)
         self.count = len(materials)
         _native.context().load_materials(self.fac, self.tex)
