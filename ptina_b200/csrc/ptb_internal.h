@@ -70,6 +70,7 @@ struct ptb_ctx {
     float4* d_texels = nullptr;     // arena           image.py:17
     SceneParams h_params{};         // host mirror
     SceneParams* d_params = nullptr;
+    SceneCache* d_cache = nullptr;  // per-scene constants derived from d_params (k_prepare_cache)
     bool params_dirty = true;
     float h_w2v[16]{};
 

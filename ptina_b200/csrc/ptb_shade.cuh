@@ -354,6 +354,82 @@ PTB_D LitSample light_sample(const SceneParams* P, V3 hitpos, V3 samp) {
     }
     return ret;
 }
+// ---- per-scene constants hoisted out of the per-vertex code (k_prepare_cache): the f32 expressions below are the ones
+// material_get / disney_init / light_hit / light_sample evaluate per call, computed once with the same operations -> same bits.
+struct LightCache { V3 dirx, diry, nrm_hit, nrm_smp; float nsqx, nsqy, area, rad2; };
+struct SceneCache {
+    Disney mat[PTB_MAX_MATERIALS + 1];          // [mtlid], last = the default material (mtlid -1); valid where plain != 0
+    int plain[PTB_MAX_MATERIALS + 1];           // no textured slot: the material does not depend on (u, v)
+    LightCache light[PTB_MAX_LIGHTS + 1];
+};
+PTB_D LightCache light_cache(const LightRec& L) {
+    LightCache c;
+    c.dirx = matvec(L.axes, mk3(L.size, 0.0f, 0.0f));
+    c.diry = matvec(L.axes, mk3(0.0f, L.size, 0.0f));
+    c.nrm_hit = normalized(cross(c.dirx, c.diry));
+    c.nrm_smp = matvec(L.axes, mk3(0.0f, 0.0f, 1.0f));
+    c.nsqx = norm_sqr(c.dirx); c.nsqy = norm_sqr(c.diry);
+    c.rad2 = L.size * L.size;
+    c.area = L.type == 1 ? PTB_PI * (L.size * L.size) : 4.0f * (L.size * L.size);
+    return c;
+}
+// light_hit with the hoisted constants (same arithmetic as light_hit / area_intersect above)
+PTB_D LitHit light_hit_cached(const SceneParams* P, const SceneCache* SC, V3 ro, V3 rd) {
+    LitHit ret; ret.hit = 0; ret.dis = PTB_INF; ret.pdf = 0.0f; ret.color = v3s(0.0f);
+    int n = P->nlights;
+    for (int i = 0; i < n; i++) {
+        const LightRec& L = P->lights[i];
+        const LightCache& C = SC->light[i];
+        float t = 0.0f, area = 0.0f;
+        if (L.type == 1) {
+            t = sphere_intersect(L.pos, C.rad2, ro, rd);
+            area = C.area;
+        } else if (L.type == 2) {
+            float NoD = dot(C.nrm_hit, rd);
+            if (NoD > PTB_EPS) {
+                float tt = dot(C.nrm_hit, L.pos - ro) / NoD;
+                V3 hd = ro + tt * rd - L.pos;
+                float u = dot(hd, C.dirx) / C.nsqx;
+                float v = dot(hd, C.diry) / C.nsqy;
+                if (-1.0f < u && u < 1.0f && -1.0f < v && v < 1.0f) { t = tt; area = C.area; }
+            }
+        }
+        if (0.0f < t && t < ret.dis) {
+            ret.dis = t; ret.pdf = (t * t) / area; ret.color = L.color; ret.hit = 1;
+            break;
+        }
+    }
+    return ret;
+}
+PTB_D LitSample light_sample_cached(const SceneParams* P, const SceneCache* SC, V3 hitpos, V3 samp) {
+    LitSample ret; ret.dis = PTB_INF; ret.dir = v3s(0.0f); ret.pdf = 0.0f; ret.color = v3s(0.0f);
+    int n = P->nlights;
+    if (n != 0) {
+        int i = clampi(ifloor(samp.z * (float)n), 0, n);   // inclusive upper clamp as in the reference
+        const LightRec& L = P->lights[i];
+        const LightCache& C = SC->light[i];
+        V3 color = L.color, litpos = v3s(PTB_INF), nrm = v3s(0.0f);
+        float area = 0.0f;
+        if (L.type == 1) {
+            litpos = L.pos + L.size * spherical(samp.x, samp.y);
+            area = C.area;
+        } else if (L.type == 2) {
+            V3 disp = matvec(L.axes, mk3(samp.x * 2.0f - 1.0f, samp.y * 2.0f - 1.0f, 0.0f));
+            nrm = C.nrm_smp;
+            litpos = L.pos + L.size * disp;
+            area = C.area;
+        }
+        V3 toli = litpos - hitpos;
+        float dis = norm(toli);
+        V3 dir = toli / dis;
+        float pdf = (dis * dis) / area;
+        color = color / pdf;
+        if (any_ne0(nrm)) color = color * dot_or_zero(nrm, dir);
+        ret.dis = dis; ret.dir = dir; ret.pdf = pdf; ret.color = color;
+    }
+    return ret;
+}
+
 // ---- light/world.py:22-29 WorldLight.at + common.py:234-239 dir2tex ----------------------------------------------------------
 PTB_D V3 world_at(const SceneParams* P, const float4* __restrict__ texels, V3 dir) {
     V4 fac = mk4(P->world_fac[0], P->world_fac[1], P->world_fac[2], P->world_fac[3]);

@@ -164,11 +164,24 @@ PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict_
 }
 
 // ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
+// per-scene constants (materials without textures, light frames), recomputed whenever the parameters are uploaded
+__global__ void k_prepare_cache(const SceneParams* __restrict__ P, const float4* __restrict__ texels, SceneCache* SC) {
+    int i = threadIdx.x;
+    if (i <= PTB_MAX_MATERIALS) {
+        int mtlid = i == PTB_MAX_MATERIALS ? -1 : i;
+        bool plain = true;
+        if (mtlid >= 0) for (int s = 0; s < PTB_NSLOTS; s++) plain = plain && P->mat_tex[mtlid][s] == -1;
+        SC->plain[i] = plain;
+        if (plain) SC->mat[i] = material_get(P, texels, mtlid, 0.0f, 0.0f);
+    }
+    if (i <= PTB_MAX_LIGHTS) SC->light[i] = light_cache(P->lights[i]);
+}
+
 #ifndef PTB_SHADE_MINBLOCKS
 #define PTB_SHADE_MINBLOCKS 8
 #endif
 template <int ENGINE>
-__global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneParams* __restrict__ P, const float4* __restrict__ texels, const float* __restrict__ verts,
+__global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
     __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                 rng.tab = rngtab + (size_t)s * dim; rng.base = wanghash2(x, y); rng.dim = dim;
             }
             // path.py:31-35 / brute.py:41-43
-            LitHit lit = light_hit(P, ro, rd);
+            LitHit lit = light_hit_cached(P, SC, ro, rd);
             if (lit.hit != 0 && (!hit || lit.dis < h4.x)) {
                 if (ENGINE == PTB_ENGINE_PATH) {
                     float mis = power_heuristic(last_pdf, lit.pdf);
@@ -213,7 +226,10 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                 avoid_slot = __ldg(&slot_of[hit_index]);
                 V3 hitpos, normal; float tu, tv; int mtlid;
                 shading_frame(verts, mtlids, hit_index, h4.y, h4.z, ro, rd, h4.x, &hitpos, &normal, &tu, &tv, &mtlid);
-                Disney mat = material_get(P, texels, mtlid, tu, tv);
+                const int mslot = mtlid < 0 ? PTB_MAX_MATERIALS : mtlid;
+                Disney mat;
+                if (SC->plain[mslot]) mat = SC->mat[mslot];              // untextured: precomputed with the same arithmetic
+                else mat = material_get(P, texels, mtlid, tu, tv);
                 float sign = -dot(rd, normal);                            // path.py:44-46 (recomputed on the flipped normal)
                 if (sign < 0.0f) normal = -normal;
                 V3 wi = -rd;
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                     c0 = 0;
                     // path.py:48-56 next-event estimation
                     V3 ls = mk3(run.draw(c0), run.draw(c0 + 1), run.draw(c0 + 2));
-                    LitSample li = light_sample(P, hitpos, ls);
+                    LitSample li = light_sample_cached(P, SC, hitpos, ls);
                     if (any_gt(li.color, 0.0f)) {
                         V3 brdf_clr = disney_brdf(mat, normal, sign, wi, li.dir);
                         float brdf_pdf = vavg(brdf_clr);                  // sic: path.py:53
@@ -615,6 +631,7 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
+    PTB_CUDA(cudaMalloc(&c->d_cache, sizeof(SceneCache)));
     int occ = 0;
     PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
@@ -631,6 +648,8 @@ int ptb_wf_upload_params(ptb_ctx* c) {
     c->h_params.nx = c->nx; c->h_params.ny = c->ny;
     // pageable host source: the copy is staged before the call returns, so later host edits cannot race it
     PTB_CUDA(cudaMemcpyAsync(c->d_params, &c->h_params, sizeof(SceneParams), cudaMemcpyHostToDevice, c->stream));
+    k_prepare_cache<<<1, 128, 0, c->stream>>>(c->d_params, c->d_texels, c->d_cache);
+    c->launches++;
     c->params_dirty = false;
     return 0;
 }
@@ -665,7 +684,7 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
         launch_extend(c, S, policy, c->xq[cur], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
         ptb_stage_end(c);
         ptb_stage_begin(c, ST_SHADE);
-        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
+        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
                                                             c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
         ptb_stage_end(c);
         c->launches += 1;
