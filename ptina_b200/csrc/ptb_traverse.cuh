@@ -156,19 +156,7 @@ PTB_D RayCons ray_cons(V3 o, V3 d) {
     return R;
 }
 // *lb: lower bound of the reference's tnear for this box (valid whether or not the box is hit); returns false only if the
-// reference's test certainly fails.
-PTB_D bool slab_cons(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayCons& R, float* lb) {
-    const float x1 = __fmaf_rn(lox, R.r.x, R.nc.x), x2 = __fmaf_rn(hix, R.r.x, R.nc.x);
-    const float y1 = __fmaf_rn(loy, R.r.y, R.nc.y), y2 = __fmaf_rn(hiy, R.r.y, R.nc.y);
-    const float z1 = __fmaf_rn(loz, R.r.z, R.nc.z), z2 = __fmaf_rn(hiz, R.r.z, R.nc.z);
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
-    const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -R.a2);
-    const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
-    *lb = l;
-    return !(l > ub);
-}
-// The same, plus *sure = the reference's test CERTAINLY passes: an upper bound of its tnear is <= a lower bound of its tfar
+// reference's test certainly fails.  *sure = the reference's test CERTAINLY passes: an upper bound of its tnear is <= a lower bound of its tfar
 // (tnear_ref <= tn(1+8u) + a2,  tfar_ref >= tf - 8u|tf|, a2 carrying both absolute terms).  A triangle whose gate is `sure` needs
 // no exact gate test; only rays grazing the gate (difference within ~1e-6 relative) are ambiguous.
 PTB_D bool slab_cons2(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayCons& R, float* lb, bool* sure) {
