@@ -12,6 +12,7 @@
 namespace {
 
 constexpr int BLK = 256;
+#define PTB_SMALL_TREE 8192          /* internal nodes up to which the box sweeps run in one block */
 
 __device__ __forceinline__ void atomicMinF(float* a, float v) {
     if (v >= 0.0f) atomicMin((int*)a, __float_as_int(v)); else atomicMax((unsigned*)a, __float_as_uint(v));
@@ -34,7 +35,7 @@ __device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int f
 __global__ void k_init_scalars(float* s) {
     s[0] = s[1] = s[2] = PTB_INF;
     s[3] = s[4] = s[5] = -PTB_INF;
-    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0;
+    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0; ((int*)s)[13] = 0;
 }
 
 // lbvh.py:172-176: bounds of the triangle CENTRES (atomic min/max; exact, order-free)
@@ -165,11 +166,10 @@ __device__ __forceinline__ void face_box(const float* __restrict__ verts, int fa
 // lbvh.py:272-294 genAABBSubstep as a Jacobi sweep: a node becomes ready in sweep `stamp` iff both children
 // were ready BEFORE this sweep (stamp < current), so there is no intra-sweep race.  Also carries the slot range
 // and height used for validation.
-__global__ void __launch_bounds__(BLK) k_aabb_sweep(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child, int n, int stamp,
-                                                    float* bmin, float* bmax, int* ready, int2* range, int* height, int* scal) {
-    int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= n - 1) return;
-    if (ready[i] != 0) return;
+// returns true if node i is still not ready after this attempt
+__device__ __forceinline__ bool aabb_try(int i, const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child, int n, int stamp,
+                                         float* bmin, float* bmax, int* ready, int2* range, int* height, int* scal) {
+    if (ready[i] != 0) return false;
     int2 ch = child[i];
     V3 lo[2], hi[2]; int2 rg[2]; int hg[2];
     bool ok = true;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(BLK) k_aabb_sweep(const float* __restrict__ ve
             rg[k] = range[j]; hg[k] = height[j];
         }
     }
-    if (!ok) { atomicAdd(&scal[8], 1); return; }
+    if (!ok) return true;
     V3 l = vmin(lo[0], lo[1]), h = vmax(hi[0], hi[1]);
     bmin[3 * i] = l.x; bmin[3 * i + 1] = l.y; bmin[3 * i + 2] = l.z;
     bmax[3 * i] = h.x; bmax[3 * i + 1] = h.y; bmax[3 * i + 2] = h.z;
@@ -198,6 +198,27 @@ __global__ void __launch_bounds__(BLK) k_aabb_sweep(const float* __restrict__ ve
     if (!(rg[0].y < rg[1].x)) scal[9] = 1;     // child0 must cover lower slots than child1
     if (i == 0) scal[10] = height[i];
     ready[i] = stamp;
+    return false;
+}
+__global__ void __launch_bounds__(BLK) k_aabb_sweep(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child, int n, int stamp,
+                                                    float* bmin, float* bmax, int* ready, int2* range, int* height, int* scal) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    if (aabb_try(i, verts, leaf, child, n, stamp, bmin, bmax, ready, range, height, scal)) atomicAdd(&scal[8], 1);
+}
+// small trees: every sweep in ONE block (a __syncthreads between sweeps instead of a launch and a host poll each).
+// scal[8] = nodes still not ready at the end, scal[13] = sweeps used.
+__global__ void __launch_bounds__(1024) k_aabb_all(const float* __restrict__ verts, const int* __restrict__ leaf, const int2* __restrict__ child, int n,
+                                                   float* bmin, float* bmax, int* ready, int2* range, int* height, int* scal) {
+    int remaining = 1, stamp = 0;
+    while (remaining != 0 && stamp < 64) {
+        stamp++;
+        int mine = 0;
+        for (int i = threadIdx.x; i < n - 1; i += 1024) mine += aabb_try(i, verts, leaf, child, n, stamp, bmin, bmax, ready, range, height, scal) ? 1 : 0;
+        __threadfence_block();
+        remaining = __syncthreads_count(mine != 0);
+    }
+    if (threadIdx.x == 0) { scal[8] = remaining; scal[13] = stamp; }
 }
 
 __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parentcnt, int n, int* scal) {
@@ -280,11 +301,8 @@ __global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, i
 // traversal boxes, level by level (`ready` holds the sweep in which the reference box of a node was completed, so the children
 // of a node of level `stamp` belong to earlier levels): union of the inflated bounds of the unlisted leaves below the node.
 // Empty = (lo, hi) = (+1e30, -1e30).
-__global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ child, const int* __restrict__ ready, int n, int stamp,
-                                                    const float* __restrict__ bmin, const float* __restrict__ bmax,
-                                                    const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* __restrict__ nlo, float4* __restrict__ nhi) {
-    int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= n - 1 || ready[i] != stamp) return;
+__device__ __forceinline__ void tbox_node(int i, const int2* __restrict__ child, int n, const float* __restrict__ bmin, const float* __restrict__ bmax,
+                                          const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* nlo, float4* nhi) {
     int2 ch = child[i];
     V3 lo = v3s(1e30f), hi = v3s(-1e30f);
     int must = 0;          // an ill-conditioned leaf below: its depth obeys no bound, so nothing above it may be culled by distance
@@ -292,6 +310,7 @@ __global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ chi
     for (int k = 0; k < 2; k++) {
         int c = k == 0 ? ch.x : ch.y;
         float4 a, b;
+        if (c < 0 || c >= 2 * n - 1) continue;         // corrupted hierarchy (reported by the build)
         if (c < n) {
             a = tlo[c]; b = thi[c];
             const int fl = __float_as_int(a.w);
@@ -301,6 +320,23 @@ __global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ chi
         lo = vmin(lo, mk3(a.x, a.y, a.z)); hi = vmax(hi, mk3(b.x, b.y, b.z));
     }
     nlo[i] = make_float4(lo.x, lo.y, lo.z, __int_as_float(must)); nhi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+}
+__global__ void __launch_bounds__(BLK) k_tbox_level(const int2* __restrict__ child, const int* __restrict__ ready, int n, int stamp,
+                                                    const float* __restrict__ bmin, const float* __restrict__ bmax,
+                                                    const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* nlo, float4* nhi) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1 || ready[i] != stamp) return;
+    tbox_node(i, child, n, bmin, bmax, tlo, thi, nlo, nhi);
+}
+__global__ void __launch_bounds__(1024) k_tbox_all(const int2* __restrict__ child, const int* __restrict__ ready, int n, const int* __restrict__ scal,
+                                                   const float* __restrict__ bmin, const float* __restrict__ bmax,
+                                                   const float4* __restrict__ tlo, const float4* __restrict__ thi, float4* nlo, float4* nhi) {
+    const int levels = scal[13];
+    for (int lvl = 1; lvl <= levels; lvl++) {
+        for (int i = threadIdx.x; i < n - 1; i += 1024) if (ready[i] == lvl) tbox_node(i, child, n, bmin, bmax, tlo, thi, nlo, nhi);
+        __threadfence_block();
+        __syncthreads();
+    }
 }
 // packed 64-byte traversal node: both children's traversal boxes and ids (-1 = nothing below: listed / never-hit leaf or an
 // internal node with an empty box); per leaf slot: its gate (parent) and the gate's REFERENCE box (bmin/bmax of the parent).
@@ -404,6 +440,12 @@ int ptb_lbvh_build(ptb_ctx* c) {
         while ((1 << first_check) < n) first_check++;   // a tree over n leaves is at least log2(n) high
         int remaining = -1;
         int h_scal[16];
+        const bool small = n - 1 <= PTB_SMALL_TREE;
+        if (small) {
+            k_aabb_all<<<1, 1024, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, n, c->d_bmin, c->d_bmax, c->d_ready, c->d_range, c->d_height, c->d_scalars);
+            c->launches++;
+            remaining = 0;      // read back with the final synchronisation below
+        } else
         for (sweeps = 1; sweeps <= 64; sweeps++) {
             PTB_CUDA(cudaMemsetAsync(&c->d_scalars[8], 0, sizeof(int), st));
             k_aabb_sweep<<<nblk(n - 1), BLK, 0, st>>>(c->d_verts, c->d_leaf, c->d_child, n, sweeps, c->d_bmin, c->d_bmax, c->d_ready, c->d_range, c->d_height, c->d_scalars);
@@ -425,9 +467,10 @@ int ptb_lbvh_build(ptb_ctx* c) {
         // traversal structure: inflated leaf bounds, always-test list, pruned traversal boxes, packed nodes
         k_tri_prep<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, scal, c->d_tlo, c->d_thi);
         k_build_list<<<1, 1024, 0, st>>>(c->d_tlo, n, PTB_LIST_CAP, c->d_list, c->d_scalars);
-        for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
+        if (small) k_tbox_all<<<1, 1024, 0, st>>>(c->d_child, c->d_ready, n, c->d_scalars, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
+        else for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
         k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_bmin, c->d_bmax, n, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_nodes, c->d_gate, c->d_gbox);
-        c->launches += 4 + sweeps;
+        c->launches += small ? 5 : 4 + sweeps;
     }
     if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }
     PTB_CUDA(cudaEventRecord(e1, st));
@@ -448,6 +491,15 @@ int ptb_lbvh_build(ptb_ctx* c) {
         c->root_must = 0;
         if (h_troot[0] <= h_troot[4]) { int m; memcpy(&m, &h_troot[3], 4); c->root_must = m != 0; }
         if (h_troot[0] <= h_troot[4]) for (int k = 0; k < 3; k++) c->scene_abs = fmaxf(c->scene_abs, fmaxf(fabsf(h_troot[k]), fabsf(h_troot[4 + k])));
+        if (n > 1 && n - 1 <= PTB_SMALL_TREE) {
+            sweeps = h_scal[13];
+            if (h_scal[8] != 0) {
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                c->tree_info.aabb_sweeps = sweeps;
+                ptb_set_error("AABB step never stop! hierarchy corrupted?");
+                return 2;
+            }
+        }
         valid = (n > 1) && h_scal[9] == 0;
         depth = valid ? h_scal[10] : 0;
         c->list_n = n > 1 ? h_scal[11] : 0;
