@@ -40,9 +40,10 @@ struct ExpQ { float4* e[PTB_EXP_K]; };
 // device-side control block: queue sizes and work cursors
 struct Ctrl {
     int n_in;        // entries in the active queue being consumed
-    int n_out;       // entries appended to the next active queue
-    int n_shadow;    // entries in the shadow queue
-    int cur_extend, cur_shadow;
+    int cur_extend;
+    int n_out;       // entries appended to the next active queue   } 8-byte aligned pair: shade reserves both with ONE 64-bit
+    int n_shadow;    // entries in the shadow queue                 } atomic per block (low word n_out, high word n_shadow)
+    int cur_shadow;
     int pad[3];
     int n_tree[2];   // entries of the tree queue written by k_trace_pre: [0] extend, [1] shadow / taps
     int cur_tree[2];

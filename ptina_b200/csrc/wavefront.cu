@@ -92,6 +92,25 @@ PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     return pos;
 }
 
+// two queues at once (next extend queue + shadow queue): one 64-bit atomic per block on the adjacent counters (n_out, n_shadow)
+PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 * BLK/32] */, unsigned long long* s_base, int* pa, int* pb) {
+    const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_warp[w] = __popc(ma); s_warp[BLK / 32 + w] = __popc(mb); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ta = 0, tb = 0;
+#pragma unroll
+        for (int i = 0; i < BLK / 32; i++) { int c = s_warp[i]; s_warp[i] = ta; ta += c; c = s_warp[BLK / 32 + i]; s_warp[BLK / 32 + i] = tb; tb += c; }
+        *s_base = (ta | tb) ? atomicAdd(reinterpret_cast<unsigned long long*>(counter_pair), (unsigned long long)(unsigned)ta | ((unsigned long long)(unsigned)tb << 32)) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long base = *s_base;
+    *pa = fa ? (int)(unsigned)base + s_warp[w] + __popc(ma & ((1u << lane) - 1u)) : -1;
+    *pb = fb ? (int)(unsigned)(base >> 32) + s_warp[BLK / 32 + w] + __popc(mb & ((1u << lane) - 1u)) : -1;
+    __syncthreads();
+}
+
 // ---- sampling/sobol.py:99-105 in closed form: X_k = XOR_{b in gray(k)} V[b+1];  P = X / 2^32 (sobol.py:19-29) ---------
 __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, int count, int stride, float* __restrict__ P) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
     __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
+    __shared__ int s_warp2[2 * (BLK / 32)]; __shared__ unsigned long long s_base2;
     const int count = ctrl->n_in;
     const int rounded = (count + BLK - 1) / BLK * BLK;
     for (int i0 = blockIdx.x * BLK; i0 < rounded; i0 += gridDim.x * BLK) {
@@ -270,13 +290,14 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
             }
             st.result[p] = make_float4(result.x, result.y, result.z, last_pdf);
         }
-        int pos = block_append(alive, &ctrl->n_out, s_warp, &s_base);
+        int pos, ps = -1;
+        if (ENGINE == PTB_ENGINE_PATH) block_append2(alive, want_shadow, &ctrl->n_out, s_warp2, &s_base2, &pos, &ps);
+        else pos = block_append(alive, &ctrl->n_out, s_warp, &s_base);
         if (alive) {
             q_out.o[pos] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
             q_out.d[pos] = make_float4(next_d.x, next_d.y, next_d.z, __int_as_float(avoid_slot));   // avoid = hit.index (as its leaf slot)
         }
         if (ENGINE == PTB_ENGINE_PATH) {
-            int ps = block_append(want_shadow, &ctrl->n_shadow, s_warp, &s_base);
             if (want_shadow) {
                 q_shadow.o[ps] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
                 q_shadow.d[ps] = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, sh_dis);
