@@ -255,6 +255,10 @@ PTB_D Node64 ld_node256(const Node64* p) {
 }
 
 #define PTB_PQ 4                    /* pending-leaf ring entries per lane */
+#ifndef PTB_VOTE_N
+#define PTB_VOTE_N 1                /* node step iff PTB_VOTE_N * (lanes ready for one) > PTB_VOTE_L * (lanes with a pending leaf) */
+#define PTB_VOTE_L 2
+#endif
 #ifndef PTB_NODE_REPS
 #define PTB_NODE_REPS 1             /* node steps per vote */
 #endif
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
             continue;
         }
         if ((mn | ml) == 0u) break;                    // exhausted and nothing in flight
-        if (__popc(mn) > __popc(ml)) {
+        if (__popc(mn) * PTB_VOTE_N > __popc(ml) * PTB_VOTE_L) {
             // ---- node step: one 64-byte node, both children's slab tests ----------------------------------------------------------------------
 #pragma unroll 1
             for (int rep = 0; rep < PTB_NODE_REPS; rep++)
