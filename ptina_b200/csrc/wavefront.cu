@@ -74,6 +74,7 @@ struct RngRun {
 
 // ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
 // returns the queue position reserved for this thread (-1 if !flag)
+template <int NT>
 PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     unsigned m = __ballot_sync(0xffffffffu, flag);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -83,7 +84,7 @@ PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     if (threadIdx.x == 0) {
         int tot = 0;
 #pragma unroll
-        for (int i = 0; i < BLK / 32; i++) { int c = s_warp[i]; s_warp[i] = tot; tot += c; }
+        for (int i = 0; i < NT / 32; i++) { int c = s_warp[i]; s_warp[i] = tot; tot += c; }
         *s_base = tot ? atomicAdd(counter, tot) : 0;
     }
     __syncthreads();
@@ -93,21 +94,22 @@ PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
 }
 
 // two queues at once (next extend queue + shadow queue): one 64-bit atomic per block on the adjacent counters (n_out, n_shadow)
-PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 * BLK/32] */, unsigned long long* s_base, int* pa, int* pb) {
+template <int NT>
+PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 * NT/32] */, unsigned long long* s_base, int* pa, int* pb) {
     const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { s_warp[w] = __popc(ma); s_warp[BLK / 32 + w] = __popc(mb); }
+    if (lane == 0) { s_warp[w] = __popc(ma); s_warp[NT / 32 + w] = __popc(mb); }
     __syncthreads();
     if (threadIdx.x == 0) {
         int ta = 0, tb = 0;
 #pragma unroll
-        for (int i = 0; i < BLK / 32; i++) { int c = s_warp[i]; s_warp[i] = ta; ta += c; c = s_warp[BLK / 32 + i]; s_warp[BLK / 32 + i] = tb; tb += c; }
+        for (int i = 0; i < NT / 32; i++) { int c = s_warp[i]; s_warp[i] = ta; ta += c; c = s_warp[NT / 32 + i]; s_warp[NT / 32 + i] = tb; tb += c; }
         *s_base = (ta | tb) ? atomicAdd(reinterpret_cast<unsigned long long*>(counter_pair), (unsigned long long)(unsigned)ta | ((unsigned long long)(unsigned)tb << 32)) : 0ull;
     }
     __syncthreads();
     const unsigned long long base = *s_base;
     *pa = fa ? (int)(unsigned)base + s_warp[w] + __popc(ma & ((1u << lane) - 1u)) : -1;
-    *pb = fb ? (int)(unsigned)(base >> 32) + s_warp[BLK / 32 + w] + __popc(mb & ((1u << lane) - 1u)) : -1;
+    *pb = fb ? (int)(unsigned)(base >> 32) + s_warp[NT / 32 + w] + __popc(mb & ((1u << lane) - 1u)) : -1;
     __syncthreads();
 }
 
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
                 st.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                         // last_brdf_pdf = 0
             }
         }
-        int pos = block_append(live, &ctrl->n_in, s_warp, &s_base);
+        int pos = block_append<BLK>(live, &ctrl->n_in, s_warp, &s_base);
         if (live) {
             if (renorm) rd = normalized(rd);
             xq.o[pos] = make_float4(ro.x, ro.y, ro.z, __int_as_float(p));
@@ -196,18 +198,21 @@ __global__ void k_prepare_cache(const SceneParams* __restrict__ P, const float4*
     if (i <= PTB_MAX_LIGHTS) SC->light[i] = light_cache(P->lights[i]);
 }
 
-#ifndef PTB_SHADE_MINBLOCKS
-#define PTB_SHADE_MINBLOCKS 8
+// 1024 threads per SM at 64 registers; the block size sets how many warps run the same instruction stream (the kernel is
+// ~130 KB of SASS: with many small blocks at different places of it the instruction caches thrash, ncu `stall_no_inst`)
+#ifndef PTB_SHADE_BLK
+#define PTB_SHADE_BLK 512
 #endif
+constexpr int SBLK = PTB_SHADE_BLK;
 template <int ENGINE>
-__global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
+__global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
-    __shared__ int s_warp[BLK / 32]; __shared__ int s_base;
-    __shared__ int s_warp2[2 * (BLK / 32)]; __shared__ unsigned long long s_base2;
+    __shared__ int s_warp[SBLK / 32]; __shared__ int s_base;
+    __shared__ int s_warp2[2 * (SBLK / 32)]; __shared__ unsigned long long s_base2;
     const int count = ctrl->n_in;
-    const int rounded = (count + BLK - 1) / BLK * BLK;
-    for (int i0 = blockIdx.x * BLK; i0 < rounded; i0 += gridDim.x * BLK) {
+    const int rounded = (count + SBLK - 1) / SBLK * SBLK;
+    for (int i0 = blockIdx.x * SBLK; i0 < rounded; i0 += gridDim.x * SBLK) {
         int idx = i0 + threadIdx.x;
         bool alive = false, want_shadow = false;
         int p = -1, avoid_slot = -1;
@@ -291,8 +296,8 @@ __global__ void __launch_bounds__(BLK, PTB_SHADE_MINBLOCKS) k_shade(const SceneP
             st.result[p] = make_float4(result.x, result.y, result.z, last_pdf);
         }
         int pos, ps = -1;
-        if (ENGINE == PTB_ENGINE_PATH) block_append2(alive, want_shadow, &ctrl->n_out, s_warp2, &s_base2, &pos, &ps);
-        else pos = block_append(alive, &ctrl->n_out, s_warp, &s_base);
+        if (ENGINE == PTB_ENGINE_PATH) block_append2<SBLK>(alive, want_shadow, &ctrl->n_out, s_warp2, &s_base2, &pos, &ps);
+        else pos = block_append<SBLK>(alive, &ctrl->n_out, s_warp, &s_base);
         if (alive) {
             q_out.o[pos] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
             q_out.d[pos] = make_float4(next_d.x, next_d.y, next_d.z, __int_as_float(avoid_slot));   // avoid = hit.index (as its leaf slot)
@@ -705,7 +710,7 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
         launch_extend(c, S, policy, c->xq[cur], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
         ptb_stage_end(c);
         ptb_stage_begin(c, ST_SHADE);
-        k_shade<ENGINE><<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
+        k_shade<ENGINE><<<c->sm_count * (1024 / SBLK), SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
                                                             c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
         ptb_stage_end(c);
         c->launches += 1;
