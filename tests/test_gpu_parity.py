@@ -249,6 +249,38 @@ def test_triangle_soup_matches_reference_order(gpu, kind):
         assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want), f'{kind} policy {policy}: shadow queries differ'
 
 
+def test_triangle_soup_films_identical_between_policies(gpu):
+    """Whole path-traced frames over a soup with slivers, degenerate and scene-spanning triangles: the production traversal, the
+    exact-ordered one and the literal one give bit-identical films (extend and shadow rays, five bounces)."""
+    from ptina_b200.model import ModelPool
+    from ptina_b200.tree import BVHTree
+    from ptina_b200.tools import matrix as mx
+    sc, _ = load(gpu, 'cornell_boxes', (96, 96), ref=False)          # camera, materials, light of the Cornell scene ...
+    for seed in range(40):
+        rng = np.random.default_rng(7000 + seed)
+        verts = _soup(rng, 'many_big')
+        verts[:, :3] = verts[:, :3] * np.float32(0.9) + np.float32([0.0, 2.0, 0.0])       # ... around a soup in front of it
+        nf = verts.shape[0] // 3
+        ModelPool().load(verts, rng.integers(-1, 3, nf).astype(np.int32))
+        try:
+            BVHTree().build()
+        except RuntimeError:
+            continue
+        if gpu.tree.valid:
+            break
+    assert gpu.tree.valid == 1 and gpu.tree.list_n == 32
+    films = {}
+    for policy in (_native.TRAVERSE_AUTO, _native.TRAVERSE_ORDERED_EXACT, _native.TRAVERSE_REFERENCE):
+        gpu.set_traversal(policy); gpu.sobol_reset(); worker.clear()
+        gpu.render(_native.ENGINE_PATH, 3)
+        films[policy] = gpu.get_film().copy()
+    gpu.set_traversal(_native.TRAVERSE_AUTO)
+    ref = films[_native.TRAVERSE_REFERENCE]
+    assert np.isfinite(ref).all() and (ref[..., :3] > 0).mean() > 0.5
+    for policy in (_native.TRAVERSE_AUTO, _native.TRAVERSE_ORDERED_EXACT):
+        assert np.array_equal(bits(films[policy]), bits(ref)), f'policy {policy}: {(bits(films[policy]) != bits(ref)).sum()} film words differ'
+
+
 def _random_materials(rng, m):
     p = np.zeros((m, 14), np.float32)
     p[:, 0:3] = rng.uniform(0.05, 1.0, (m, 3))
