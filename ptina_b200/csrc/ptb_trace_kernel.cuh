@@ -159,6 +159,18 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
     unsigned long long nrays = 0;
     __shared__ int s_warp[8], s_base;
+    // the always-test list in shared memory: slots, packed triangles, gate boxes (broadcast reads, no dependent global loads)
+    __shared__ int s_slot[PTB_LIST_CAP];
+    __shared__ float4 s_tri[PTB_LIST_CAP][4];
+    __shared__ float4 s_gate[PTB_LIST_CAP][2];
+    const int nlist = min(S.nlist, PTB_LIST_CAP);
+    for (int j = threadIdx.x; j < nlist * 4; j += 256) {
+        const int slot = S.list[j >> 2];
+        s_tri[j >> 2][j & 3] = reinterpret_cast<const float4*>(S.tris + slot)[j & 3];
+        if ((j & 3) < 2) s_gate[j >> 2][j & 3] = S.gbox[2 * slot + (j & 3)];
+        if ((j & 3) == 0) s_slot[j >> 2] = slot;
+    }
+    __syncthreads();
     const int rounded = (count + 255) & ~255;          // every thread of a block runs the same number of iterations
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < rounded; idx += gridDim.x * 256) {
         bool live = false;
@@ -178,17 +190,17 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                 R = ray_cons(in.ro, in.rd);
                 float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
                 bool occluded = false;
-                for (int j = 0; j < S.nlist; j++) {
-                    const int slot = S.list[j];
+                for (int j = 0; j < nlist; j++) {
+                    const int slot = s_slot[j];
                     if (slot == in.avoid_slot) continue;
-                    const Tri64 T = S.tris[slot];
+                    Tri64 T; T.a = s_tri[j][0]; T.b = s_tri[j][1]; T.c = s_tri[j][2]; T.d = s_tri[j][3];
                     if (COUNT) C.tris++;
                     float dep, s, t;
                     if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
                         const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
                         if (better) {
                             // the reference tests this triangle only if its gate passes Box.intersect: conservative, exact when grazing
-                            const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
+                            const float4 glo = s_gate[j][0], ghi = s_gate[j][1];
                             float gl; bool gsure;
                             if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], in.ro, in.rd))) {
                                 ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep;
