@@ -179,6 +179,13 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
         float delta = 0.0f;
         HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
         if (idx < count) {
+            {   // start the next iteration's record on its way (the loop is otherwise serialised on this DRAM round trip)
+                const int nxt = idx + gridDim.x * 256;
+                if (nxt < count) {
+#pragma unroll
+                    for (int k = 0; k < IO::K; k++) asm volatile("prefetch.global.L1 [%0];" ::"l"(io.rec(k) + nxt));
+                }
+            }
             fetch_direct(io, idx, &in);
             if (COUNT) nrays++;
             if (ray_is_special(in.ro, in.rd)) {

@@ -219,6 +219,10 @@ __global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* 
         V3 next_o = v3s(0.0f), next_d = v3s(0.0f), sh_dir = v3s(0.0f), sh_contrib = v3s(0.0f);
         float sh_dis = 0.0f;
         if (idx < count) {
+            {   // start the next iteration's records on their way
+                const int nxt = idx + gridDim.x * SBLK;
+                if (nxt < count) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q_in.o + nxt)); asm volatile("prefetch.global.L1 [%0];" ::"l"(q_in.d + nxt)); }
+            }
             float4 o4 = q_in.o[idx], d4 = q_in.d[idx];
             p = __float_as_int(o4.w);
             float4 h4 = st.hit[p], t4 = st.thr[p], r4 = st.result[p];
