@@ -58,16 +58,42 @@ def config_of(sc, n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe): NVML in-process every few ms
+    (nvidia_ml_py), falling back to polling nvidia-smi."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.max_mhz, self.source = index, [], False, None, 'nvidia-smi'
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            phys = int(vis.split(',')[index]) if vis and all(v.strip().isdigit() for v in vis.split(',')) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, 'nvml'
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        mhz = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        bits = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+        return [str(mhz), str(self.max_mhz)] + ['Active' if r & bits[k] else 'Not Active' for k in self.NAMES]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._nvml_sample())
+                    time.sleep(0.004)
+                    continue
                 out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -78,12 +104,11 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable']}
         mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples if len(s) > 2 + i)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith('active') for s in self.samples if len(s) > 2 + i)]
         return {'sm_mhz': mhz[len(mhz) // 2] if mhz else None, 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                'reasons': reasons, 'samples': len(self.samples)}
+                'reasons': reasons, 'samples': len(self.samples), 'source': self.source}
 
 
 def cpu_reference(sc, seconds, threads=0):
