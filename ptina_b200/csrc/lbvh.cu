@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
 
 // ---- traversal tree (ptb_traverse.cuh "traversal structure") ------------------------------------------------------------------------
 // Per leaf slot: the triangle's bounds inflated by eps_T, the distance within which Face.intersect's f32 arithmetic can accept a
-// point outside the triangle (derivation in DESIGN.md "Leaf boxes"):
+// point outside the triangle (derivation in DESIGN.md section 10):
 //   eps_T = 256u * cond * (|u| + |v|) + 64u * (|v0|_inf + |u| + |v|),  cond = uu*vv / |D| = 1 / sin^2(angle(u, v)),  u = 2^-24
 // valid while cond * (36 + 20 * max(|u|/|v|, |v|/|u|)) <= 1e6.  Flags (w of tlo): 1 = NEVER (D == 0 or not finite: s, t are
 // inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> the leaf is bounded by its GATE box instead, the
