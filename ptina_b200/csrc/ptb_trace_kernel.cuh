@@ -285,7 +285,7 @@ PTB_D Node64 ld_node256(const Node64* p) {
 #define PTB_TRACE_BLK_S 768         /* threads of the shared-memory-resident variant (one CTA per SM) */
 #endif
 #ifndef PTB_TRACE_MINB
-#define PTB_TRACE_MINB 6            /* resident CTAs per SM the global-memory variant is compiled for (80 registers, no spills) */
+#define PTB_TRACE_MINB 7            /* resident CTAs per SM the global-memory variant is compiled for (72 registers) */
 #endif
 
 // dynamic shared memory layout of k_trace_tree (bytes), shared by the kernel and the host launch code
