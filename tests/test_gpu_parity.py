@@ -88,6 +88,39 @@ def test_secondary_rays_match_reference_order(gpu, name):
         assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want)
 
 
+@pytest.mark.parametrize('name', ['cornell_monkey', 'mega_small'])
+def test_literal_traversal_work_counts_equal_the_oracle(gpu, name):
+    """Integer parity of the work itself: under the literal policy (lbvh.py:313-347) the GPU pops, box-tests and triangle-tests
+    exactly as often as the oracle on the same rays, and needs the same stack depth (incoherent secondary rays with an avoid id,
+    and the primary rays of one sample)."""
+    sc, o = load(gpu, name, SMALL[name])
+    rng = np.random.default_rng(5)
+    m = 5000
+    verts = np.asarray(sc['vertices'], np.float32)[:, :3].reshape(-1, 3, 3)
+    f = rng.integers(0, verts.shape[0], m)
+    w = rng.dirichlet([1, 1, 1], m).astype(np.float32)
+    org = (verts[f] * w[:, :, None]).sum(1)
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, d], 1).astype(np.float32)
+    want = o.intersect(rays, f.astype(np.int32), counters=True)['counters']
+    keys = ('node_visits', 'box_tests', 'tri_tests', 'max_stack')
+    gpu.set_counting(True)
+    try:
+        gpu.reset_counters()
+        gpu.intersect(rays, f.astype(np.int32), _native.TRAVERSE_REFERENCE)
+        got = gpu.counters()
+        assert got['rays'] == m and {k: got[k] for k in keys} == {k: want[k] for k in keys}
+        # the primary rays of one sample (coherent, no avoid id)
+        prim = o.primary(66, trace=False)['rays']
+        want = o.intersect(prim, counters=True)['counters']
+        gpu.reset_counters()
+        gpu.intersect(prim, None, _native.TRAVERSE_REFERENCE)
+        got = gpu.counters()
+        assert got['rays'] == prim.shape[0] and {k: got[k] for k in keys} == {k: want[k] for k in keys}
+    finally:
+        gpu.set_counting(False)
+
+
 @pytest.mark.parametrize('name', ['cornell_boxes', 'cornell_monkey', 'mega_small'])
 def test_adversarial_rays_match_reference_order(gpu, name):
     """Rays built to stress the conservative box test + exact gate test of the production kernel: axis-parallel and nearly
