@@ -116,6 +116,8 @@ def cpu_reference(sc, seconds, threads=0):
     the workload's resolution, as many samples per pixel as fit in ~`seconds`."""
     import oracle
     from ptina_b200 import scenes
+    if threads <= 0:            # every core this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     ref = oracle.Oracle()
     scenes.apply(ref, sc)
     eng = oracle.ENGINE_BRUTE if sc['engine'] == 'brute' else oracle.ENGINE_PATH
@@ -123,7 +125,7 @@ def cpu_reference(sc, seconds, threads=0):
     n = int(max(1, min(sc['spp'], seconds / max(dt1, 1e-3))))
     t0 = time.time(); cnt = ref.render(eng, n, nthreads=threads); dt = time.time() - t0
     nx, ny = sc['size']
-    return {'value': cnt['rays'] / dt / 1e6, 'unit': UNIT, 'cores': oracle.num_threads(), 'kind': 'port',
+    return {'value': cnt['rays'] / dt / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
             'sample': f"{n} spp of the {nx}x{ny} frame ({cnt['rays']} rays, {dt:.2f} s), OpenMP over pixel rows",
             'spp_per_s': n / dt, 'seconds': dt, 'rays': cnt['rays'],
             'note': 'C++ restatement of the Taichi algorithm (unordered DFS, per-pixel megakernel); Taichi is not installable in this image'}
@@ -304,7 +306,7 @@ def run_gpu(args):
                 'counters_per_step_rank0': cnt,
                 'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms},
                 'clocks': sampler.summary()}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # rank 0 at N=1 only (torchrun also pins OMP_NUM_THREADS=1)
             line['cpu_baseline'] = {k: v for k, v in cpu_reference(sc, args.cpu_seconds).items() if k in ('value', 'unit', 'cores', 'kind', 'sample', 'spp_per_s', 'note')}
         print(json.dumps(line), flush=True)
     if world > 1:
