@@ -58,7 +58,7 @@ def build(force=False, verbose=False, defines=(), out=None):
             sys.stderr.write(log)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [nvcc] + ccbin + ['-shared', '-o', out] + objs + ['-lcudart']
+    cmd = [nvcc] + ccbin + ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs + ['-lcudart']
     subprocess.check_call(cmd, env=env)
     return out
 

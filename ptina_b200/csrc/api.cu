@@ -14,7 +14,6 @@ void ptb_set_error(const char* fmt, ...) {
 TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
     S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.nlo = c->d_nlo; S.nhi = c->d_nhi; S.list = c->d_list; S.nlist = c->list_n; S.scene_abs = c->scene_abs; S.root_must = c->root_must; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
-    for (int k = 0; k < 3; k++) { S.root_lo[k] = c->root_lo[k]; S.root_hi[k] = c->root_hi[k]; }
     return S;
 }
 int ptb_effective_policy(const ptb_ctx* c, int requested) {

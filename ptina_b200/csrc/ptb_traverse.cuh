@@ -47,7 +47,6 @@ struct TraceScene {
     const float* __restrict__ bmin;      // [n-1][3]
     const float* __restrict__ bmax;      // [n-1][3]
     const int2* __restrict__ child;      // [n-1]
-    float root_lo[3], root_hi[3];
     int n;
 };
 
