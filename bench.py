@@ -111,7 +111,7 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.samples), 'source': self.source}
 
 
-def cpu_reference(sc, seconds, threads=0):
+def cpu_reference(sc, seconds, threads=0, max_frames=1):
     """The oracle (CPU restatement of the reference algorithm) on all host threads, on a bounded sample: whole frames at
     the workload's resolution, as many samples per pixel as fit in ~`seconds`."""
     import oracle
@@ -122,7 +122,7 @@ def cpu_reference(sc, seconds, threads=0):
     scenes.apply(ref, sc)
     eng = oracle.ENGINE_BRUTE if sc['engine'] == 'brute' else oracle.ENGINE_PATH
     t0 = time.time(); cnt = ref.render(eng, 1, nthreads=threads); dt1 = time.time() - t0       # warm-up + calibration
-    n = int(max(1, min(sc['spp'], seconds / max(dt1, 1e-3))))
+    n = int(max(1, min(sc['spp'] * max_frames, seconds / max(dt1, 1e-3))))
     t0 = time.time(); cnt = ref.render(eng, n, nthreads=threads); dt = time.time() - t0
     nx, ny = sc['size']
     return {'value': cnt['rays'] / dt / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
@@ -307,7 +307,7 @@ def run_gpu(args):
                 'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms},
                 'clocks': sampler.summary()}
         if not args.no_cpu and world == 1:      # rank 0 at N=1 only (torchrun also pins OMP_NUM_THREADS=1)
-            line['cpu_baseline'] = {k: v for k, v in cpu_reference(sc, args.cpu_seconds).items() if k in ('value', 'unit', 'cores', 'kind', 'sample', 'spp_per_s', 'note')}
+            line['cpu_baseline'] = {k: v for k, v in cpu_reference(sc, args.cpu_seconds, max_frames=8).items() if k in ('value', 'unit', 'cores', 'kind', 'sample', 'spp_per_s', 'note')}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
