@@ -31,11 +31,11 @@ __device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int f
 }
 
 // scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height,
-// [11] always-test list length, [12] list overflow
+// [11] always-test list length, [12] list overflow, [13] sweeps, [14] node planes outside the quantisation grid
 __global__ void k_init_scalars(float* s) {
     s[0] = s[1] = s[2] = PTB_INF;
     s[3] = s[4] = s[5] = -PTB_INF;
-    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0; ((int*)s)[13] = 0;
+    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0; ((int*)s)[13] = 0; ((int*)s)[14] = 0;
 }
 
 // lbvh.py:172-176: bounds of the triangle CENTRES (atomic min/max; exact, order-free)
@@ -378,6 +378,49 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const int2* __restrict__ chi
     nodes[i] = N;
 }
 
+// Node32 (ptb_traverse.cuh): the boxes of a packed node on the 15-bit grid, rounded outward.  The candidate from the f32 estimate is
+// corrected against the exact value of the plane it decodes to (base + (1 + q/32768) * ext: a 24-bit plus a 16-bit number of
+// nearby exponents, exact in double), so lo' <= lo and hi' >= hi hold as real numbers whatever the rounding of the estimate.
+// scal[14] counts planes outside the grid (cannot happen: the grid covers both root boxes; checked by the host all the same).
+struct QuantGrid { float base[3], ext[3]; };
+__device__ __forceinline__ unsigned quant_plane(float x, float base, float ext, bool up, int* bad) {
+    const double b = (double)base, e = (double)ext, xd = (double)x;
+    double t = ((xd - b) / e - 1.0) * 32768.0;
+    int q = up ? (int)ceil(t) : (int)floor(t);
+    q = q < 0 ? 0 : (q > 32767 ? 32767 : q);
+    for (int it = 0; it < 4; it++) {
+        const double pl = b + (1.0 + (double)q * (1.0 / 32768.0)) * e;
+        if (up ? pl >= xd : pl <= xd) break;
+        if (up ? q == 32767 : q == 0) break;
+        q += up ? 1 : -1;
+    }
+    const double pl = b + (1.0 + (double)q * (1.0 / 32768.0)) * e;
+    if (!(up ? pl >= xd : pl <= xd)) *bad = 1;
+    return 0x8000u | (unsigned)q;
+}
+__global__ void __launch_bounds__(BLK) k_quant_nodes(const Node64* __restrict__ nodes, int n, QuantGrid g, uint4* __restrict__ qnodes, int* __restrict__ scal) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    const Node64 N = nodes[i];
+    const int id0 = __float_as_int(N.a.w), id1 = __float_as_int(N.b.w);
+    const float lo[2][3] = {{N.a.x, N.a.y, N.a.z}, {N.c.x, N.c.y, N.c.z}}, hi[2][3] = {{N.b.x, N.b.y, N.b.z}, {N.d.x, N.d.y, N.d.z}};
+    unsigned f[12];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const bool used = (k == 0 ? id0 : id1) >= 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            int dummy = 0;
+            f[6 * k + a] = quant_plane(used ? lo[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], false, used ? &bad : &dummy);
+            f[6 * k + 3 + a] = quant_plane(used ? hi[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], true, used ? &bad : &dummy);
+        }
+    }
+    if (bad) atomicAdd(&scal[14], 1);
+    qnodes[2 * i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+    qnodes[2 * i + 1] = make_uint4(f[8] | (f[9] << 16), f[10] | (f[11] << 16), (unsigned)id0, (unsigned)id1);
+}
+
 // packed 64-byte triangle by leaf slot; u, v, n, uu, uv, vv, D are the f32 expressions of geometries.py:121-141
 __global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ verts, const int* __restrict__ leaf, int n, Tri64* tris, int* slot_of) {
     int s = blockIdx.x * BLK + threadIdx.x;
@@ -505,6 +548,36 @@ int ptb_lbvh_build(ptb_ctx* c) {
         c->list_n = n > 1 ? h_scal[11] : 0;
         c->list_overflow = n > 1 ? h_scal[12] : 0;
         for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
+        // quantised nodes for a tree too big to be resident as 64-byte nodes (wavefront.cu launch_trace_io decides the same way)
+        if (valid && ptb_tree_mode(c, n) != PTB_TREE_RESIDENT) {
+            QuantGrid g;
+            bool finite = true;
+            for (int k = 0; k < 3; k++) {
+                float lo = h_root[k], hi = h_root[3 + k];
+                if (h_troot[0] <= h_troot[4]) { lo = fminf(lo, h_troot[k]); hi = fmaxf(hi, h_troot[4 + k]); }
+                finite = finite && std::isfinite(lo) && std::isfinite(hi) && lo <= hi;
+                // plane = base + v * ext, v in [1, 2 - 2^-15]: ext a power of two, base rounded down, widened until it covers [lo, hi]
+                double ext = ldexp(1.0, (int)ceil(log2(fmax((double)hi - (double)lo, 1e-30) * 1.01)));
+                float base = 0.0f;
+                for (int it = 0; it < 8; it++, ext *= 2.0) {
+                    const double b = (double)lo - ext;
+                    base = (float)b;
+                    if ((double)base > b) base = nextafterf(base, -INFINITY);
+                    if ((double)base + ext <= (double)lo && (double)base + (2.0 - 1.0 / 32768.0) * ext >= (double)hi) break;
+                }
+                g.base[k] = base; g.ext[k] = (float)ext;
+                c->qbase[k] = base; c->qext[k] = (float)ext; c->qinv[k] = (float)(1.0 / ext);
+                finite = finite && std::isfinite(c->qext[k]) && std::isfinite(c->qinv[k]) && c->qinv[k] > 0.0f;
+            }
+            int bad = 1;
+            if (finite) {
+                k_quant_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_nodes, n, g, c->d_qnodes, c->d_scalars);
+                c->launches++;
+                PTB_CUDA(cudaMemcpyAsync(&bad, &c->d_scalars[14], sizeof(int), cudaMemcpyDeviceToHost, st));
+                PTB_CUDA(cudaStreamSynchronize(st));
+            }
+            if (bad) valid = 0;        // no usable grid (non-finite bounds): the literal traversal takes over
+        }
     }
     PTB_CUDA(cudaGetLastError());
     float ms = 0.0f;

@@ -92,6 +92,8 @@ struct ptb_ctx {
     int2* d_range = nullptr;        // (min slot, max slot) per internal node
     int32_t* d_height = nullptr;
     Node64* d_nodes = nullptr;
+    uint4* d_qnodes = nullptr;      // [2(n-1)] quantised copy of d_nodes (Node32), built for trees that are traversed out of global memory
+    float qbase[3]{}, qext[3]{1.0f, 1.0f, 1.0f}, qinv[3]{1.0f, 1.0f, 1.0f};
     Tri64* d_tris = nullptr;
     int32_t* d_slot_of = nullptr;   // face id -> leaf slot
     int32_t* d_gate = nullptr;      // leaf slot -> parent internal node (the box that gates its triangle test)
@@ -123,6 +125,7 @@ struct ptb_ctx {
     DevCounters* d_counters = nullptr;
     int counting = 0;
     int smem_optin = 0;             // opt-in shared memory per block (227 KB on B200)
+    bool quant_resident_bvh = false; // PTB_QUANT_RESIDENT_BVH=1: resident trees always as quantised nodes (testing)
     bool no_resident_bvh = false;   // PTB_NO_RESIDENT_BVH=1: never use the shared-memory-resident traversal variant
     int blocks_extend = 0, blocks_shadow = 0, blocks_ref = 0, blocks_generic = 0, blocks_exact = 0;
     std::vector<StageEvent> events;
@@ -141,6 +144,8 @@ struct ptb_ctx {
 
 TraceScene ptb_trace_scene(const ptb_ctx* c);
 int ptb_effective_policy(const ptb_ctx* c, int requested);
+enum { PTB_TREE_RESIDENT = 0, PTB_TREE_RESIDENT_QUANT = 1, PTB_TREE_GLOBAL = 2 };
+int ptb_tree_mode(const ptb_ctx* c, int n);               // wavefront.cu: where the tree kernel keeps the nodes
 
 // lbvh.cu
 int ptb_lbvh_build(ptb_ctx* c);

@@ -262,15 +262,10 @@ PTB_D void cp_async16(void* smem_dst, const void* gmem_src) {
 }
 PTB_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> PTB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-// 64-byte record through two 256-bit loads (sm_100: LDG.E.256): half the L1 wavefronts of four 128-bit loads when every lane of a
-// warp reads a different record
-PTB_D Node64 ld_node256(const Node64* p) {
-    Node64 N;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(N.a.x), "=f"(N.a.y), "=f"(N.a.z), "=f"(N.a.w), "=f"(N.b.x), "=f"(N.b.y), "=f"(N.b.z), "=f"(N.b.w) : "l"(p));
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(N.c.x), "=f"(N.c.y), "=f"(N.c.z), "=f"(N.c.w), "=f"(N.d.x), "=f"(N.d.y), "=f"(N.d.z), "=f"(N.d.w) : "l"(reinterpret_cast<const char*>(p) + 32));
-    return N;
+// 32-byte quantised node (Node32, ptb_traverse.cuh): one 256-bit load
+PTB_D void ld_qnode256(const uint4* p, uint4* a, uint4* b) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w) : "l"(p));
 }
 
 #define PTB_PQ 4                    /* pending-leaf ring entries per lane */
@@ -295,14 +290,17 @@ struct TraceSmem {
     static constexpr size_t queue = (size_t)PTB_PQ * BLK * (sizeof(int) + sizeof(float));
     static constexpr size_t fixed = tile + queue;
     __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64); }
+    __host__ __device__ static size_t qbvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * 32; }          // quantised (Node32)
 };
 
 // ---- production phase B: traversal of the tree for the rays k_trace_pre queued ----------------------------------------------------
-// SMEM = true: the packed nodes of the traversal tree (64 B per triangle) are copied into shared memory by each CTA (one CTA of
-// PTB_TRACE_BLK_S threads per SM) as four 16-byte "quarter" arrays, so that a divergent 64-byte node fetch costs ~4 x 7
-// shared-memory wavefronts instead of 4 x 32 L1 wavefronts (one per lane and 16-byte load).  Triangles, gate boxes and the
-// local-memory stack stay behind L1, which keeps ~100 KB next to the 150 KB carve-out.
-template <class IO, bool COUNT, int BLK, bool SMEM>
+// SMEM = true: the nodes of the traversal tree are copied into shared memory by each CTA (one CTA of PTB_TRACE_BLK_S threads per
+// SM), as four 16-byte "quarter" arrays of the packed 64-byte nodes (QN = false) or, for trees up to twice that size, two 16-byte
+// halves of the quantised 32-byte nodes (QN = true), so that a divergent node fetch costs shared-memory wavefronts instead of one
+// L1 wavefront per lane and 16-byte load.  Triangles, gate boxes and the local-memory stack stay behind L1, which keeps ~100 KB
+// next to the carve-out.  SMEM = false (bigger trees): quantised nodes out of global memory, one 256-bit load per step, several
+// CTAs per SM to cover the L2 latency.
+template <class IO, bool COUNT, int BLK, bool SMEM, bool QN>
 __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(TraceScene S, IO io, ExpQ xq, int* cursor, const int* count_ptr, DevCounters* ctr) {
     constexpr bool ANYHIT = IO::kAnyHit;
     constexpr int K = PTB_EXP_K;
@@ -323,8 +321,13 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<BLK>::fixed);
     if (SMEM) {
         if (blockIdx.x * PTB_TILE >= count) return;        // more CTAs than tiles of work: skip the copy
-        const float4* gn = reinterpret_cast<const float4*>(S.nodes);
-        for (int i = threadIdx.x; i < 4 * (n - 1); i += BLK) s_node[(i & 3) * (n - 1) + (i >> 2)] = gn[i];
+        if constexpr (QN) {                                 // quantised nodes: two 16-byte halves per node
+            const float4* gn = reinterpret_cast<const float4*>(S.qnodes);
+            for (int i = threadIdx.x; i < 2 * (n - 1); i += BLK) s_node[(i & 1) * (n - 1) + (i >> 1)] = gn[i];
+        } else {
+            const float4* gn = reinterpret_cast<const float4*>(S.nodes);
+            for (int i = threadIdx.x; i < 4 * (n - 1); i += BLK) s_node[(i & 3) * (n - 1) + (i >> 2)] = gn[i];
+        }
         __syncthreads();
     }
 
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     int item = -1, avoid_slot = -1;            // item >= 0: this lane owns a ray (its result is stored when the lane next goes idle)
     RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
     RayTrav Q; Q.nc1 = v3s(0.0f); Q.nc2 = v3s(0.0f);   // slab constants of the traversal-tree boxes (ray_trav)
+    RayQuant G; G.A = v3s(0.0f); G.B1 = v3s(0.0f); G.B2 = v3s(0.0f);      // the same for quantised nodes (ray_quant)
     V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
@@ -393,6 +397,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                 R.o = mk3(e0.x, e0.y, e0.z); R.d = mk3(e1.x, e1.y, e1.z); R.r = mk3(e2.x, e2.y, e2.z); R.nc = mk3(e3.x, e3.y, e3.z);
                 R.a2 = __fmaf_rn(fmaxf(fmaxf(fabsf(R.nc.x), fabsf(R.nc.y)), fabsf(R.nc.z)), PTB_CONS_KAPPA, 1e-30f);
                 Q = ray_trav(R, e2.w);
+                if constexpr (QN) G = ray_quant(S, R, Q);           // quantised nodes: R.r and Q are not used past this point
                 ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
                 if (ANYHIT) { contrib = mk3(e4.x, e4.y, e4.z); best = fminf(e4.w, PTB_INF); }
                 else {                                                      // provisional closest hit over the always-test list
@@ -422,15 +427,26 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                 if (cur == -1) { cur = (int)(unsigned)pe; cur_near = __int_as_float((int)(pe >> 32)); popped = false; }
                 if (cur_near > cull) cur = -1;          // nothing below can beat the best hit found since it was pushed / chosen
                 else {
-                    Node64 N;
-                    if (SMEM) { N.a = s_node[cur]; N.b = s_node[(n - 1) + cur]; N.c = s_node[2 * (n - 1) + cur]; N.d = s_node[3 * (n - 1) + cur]; }
-                    else N = ld_node256(S.nodes + cur);
+                    int w0, w1;                          // child ids; -1: nothing below
+                    float n0, n1;
+                    bool h0, h1;
+                    if constexpr (!QN) {
+                        Node64 N;
+                        N.a = s_node[cur]; N.b = s_node[(n - 1) + cur]; N.c = s_node[2 * (n - 1) + cur]; N.d = s_node[3 * (n - 1) + cur];
+                        w0 = __float_as_int(N.a.w); w1 = __float_as_int(N.b.w);
+                        h0 = slab_trav(N.a, N.b, R, Q, &n0); h1 = slab_trav(N.c, N.d, R, Q, &n1);
+                    } else {
+                        uint4 qa, qb;
+                        if constexpr (SMEM) { qa = reinterpret_cast<const uint4*>(s_node)[cur]; qb = reinterpret_cast<const uint4*>(s_node)[(n - 1) + cur]; }
+                        else ld_qnode256(S.qnodes + 2 * cur, &qa, &qb);
+                        w0 = (int)qb.z; w1 = (int)qb.w;
+                        h0 = slab_quant(quant_lo(qa.x), quant_hi(qa.x), quant_lo(qa.y), quant_hi(qa.y), quant_lo(qa.z), quant_hi(qa.z), G, R.a2, &n0);
+                        h1 = slab_quant(quant_lo(qa.w), quant_hi(qa.w), quant_lo(qb.x), quant_hi(qb.x), quant_lo(qb.y), quant_hi(qb.y), G, R.a2, &n1);
+                    }
                     if (COUNT) { C.nodes++; C.boxes += 2; }
-                    const int w0 = __float_as_int(N.a.w), w1 = __float_as_int(N.b.w);      // -1: nothing below
+                    h0 = h0 && w0 >= 0; h1 = h1 && w1 >= 0;
                     const int c0 = w0 & PTB_NODE_ID, c1 = w1 & PTB_NODE_ID;
                     const bool must0 = (w0 & PTB_NODE_MUST) != 0, must1 = (w1 & PTB_NODE_MUST) != 0;
-                    float n0, n1;
-                    bool h0 = slab_trav(N.a, N.b, R, Q, &n0) && w0 >= 0, h1 = slab_trav(N.c, N.d, R, Q, &n1) && w1 >= 0;
                     if (must0) n0 = 0.0f;               // an ill-conditioned triangle below: no distance bound holds
                     if (must1) n1 = 0.0f;
                     h0 = h0 && !(n0 > cull); h1 = h1 && !(n1 > cull);
@@ -467,7 +483,9 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                         if (better) {
                             const float4 glo = S.gbox[2 * slot], ghi = S.gbox[2 * slot + 1];
                             float gl; bool gsure;
-                            if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], R.o, R.d))) {
+                            RayCons Rg = R;
+                            if constexpr (QN) Rg.r = mk3(G.A.x * S.qinv[0], G.A.y * S.qinv[1], G.A.z * S.qinv[2]);     // exact: A = qext * r, qext = 2^k
+                            if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, Rg, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], R.o, R.d))) {
                                 ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot;
                                 ret.index = S.leaf[slot];                         // face id: only read when the ray is stored
                                 if (ANYHIT) { cur = -1; sp = 0; popped = false; q_count = 0; }    // occluded: done (stored when the lane is refilled)

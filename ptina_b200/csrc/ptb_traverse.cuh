@@ -48,6 +48,9 @@ struct TraceScene {
     const float* __restrict__ bmax;      // [n-1][3]
     const int2* __restrict__ child;      // [n-1]
     int n;
+    // quantised copy of `nodes` for trees that do not fit in shared memory (32 B per node, see Node32)
+    const uint4* __restrict__ qnodes;    // [2(n-1)]
+    float qbase[3], qext[3], qinv[3];    // plane = qbase + v * qext, v in [1, 2) on a 15-bit grid; qext a power of two, qinv = 1 / qext
 };
 
 struct HitRec { int hit; float depth; int index; float u, v; int slot; };
@@ -252,6 +255,44 @@ PTB_D bool tri_fast(const Tri64& T, V3 ro, V3 rd, float tlimit, float* depth, fl
     float t = div_exact(uv * wu - uu * wv, D, rD);
     *s_out = s; *t_out = t; *depth = r;
     return (0.0f <= s && s <= 1.0f) && (0.0f <= t && s + t <= 1.0f);
+}
+
+// ---- quantised traversal nodes -------------------------------------------------------------------------------------------------------
+// A tree too big for shared memory is walked out of L2, and every step waits for the slowest of a warp's 32 scattered fetches, so
+// what matters is that the whole node array stays cache resident and one fetch brings a node.  Node32 stores the two child boxes on
+// a per-axis 15-bit grid over the scene, rounded OUTWARD (the traversal tree only has to be conservative: a larger box can add
+// candidates, never lose one):  plane = qbase + v * qext,  v = 1 + q / 32768.  The 16-bit field is 0x8000 | q, so that one PRMT
+// with 0x3F000000 turns it into the f32 v, and the plane is never formed: with A = qext * r (exact, qext is a power of two) and
+// B = fma(qbase, r, nc) the slab distance is fma(v, A, B) -- the product is exact, so against fma(plane, r, nc) the only new
+// error is the rounding of B, at most u|B| per plane, which ray_quant folds into B itself.
+//   words 0-5: (lo0.x lo0.y) (lo0.z hi0.x) (hi0.y hi0.z) (lo1.x lo1.y) (lo1.z hi1.x) (hi1.y hi1.z), low half first; 6, 7: child ids
+struct RayQuant { V3 A, B1, B2; };
+PTB_D RayQuant ray_quant(const TraceScene& S, const RayCons& R, const RayTrav& Q) {
+    RayQuant G;
+    G.A = mk3(S.qext[0] * R.r.x, S.qext[1] * R.r.y, S.qext[2] * R.r.z);
+    // B is rounded once (|error| <= u|B|): moved by 4u|B| (at least 3u|B| after the rounding of this fma) to the side that pushes the
+    // plane outward -- down for the lo planes, up for the hi planes when r > 0, the other way when r < 0.  Per axis, like delta: an
+    // absolute margin shared by the axes would be scaled by the largest |1/d| and make nearly axis-parallel rays enter every box.
+    const float K4 = 2.384185791015625e-7f;        // 4u
+    const V3 k = mk3(copysignf(K4, R.r.x), copysignf(K4, R.r.y), copysignf(K4, R.r.z));
+    V3 b1 = mk3(__fmaf_rn(S.qbase[0], R.r.x, Q.nc1.x), __fmaf_rn(S.qbase[1], R.r.y, Q.nc1.y), __fmaf_rn(S.qbase[2], R.r.z, Q.nc1.z));
+    V3 b2 = mk3(__fmaf_rn(S.qbase[0], R.r.x, Q.nc2.x), __fmaf_rn(S.qbase[1], R.r.y, Q.nc2.y), __fmaf_rn(S.qbase[2], R.r.z, Q.nc2.z));
+    G.B1 = mk3(__fmaf_rn(-k.x, fabsf(b1.x), b1.x), __fmaf_rn(-k.y, fabsf(b1.y), b1.y), __fmaf_rn(-k.z, fabsf(b1.z), b1.z));
+    G.B2 = mk3(__fmaf_rn(k.x, fabsf(b2.x), b2.x), __fmaf_rn(k.y, fabsf(b2.y), b2.y), __fmaf_rn(k.z, fabsf(b2.z), b2.z));
+    return G;
+}
+PTB_D float quant_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104)); }
+PTB_D float quant_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324)); }
+PTB_D bool slab_quant(float lx, float ly, float lz, float hx, float hy, float hz, const RayQuant& G, float a2, float* lb) {
+    const float x1 = __fmaf_rn(lx, G.A.x, G.B1.x), x2 = __fmaf_rn(hx, G.A.x, G.B2.x);
+    const float y1 = __fmaf_rn(ly, G.A.y, G.B1.y), y2 = __fmaf_rn(hy, G.A.y, G.B2.y);
+    const float z1 = __fmaf_rn(lz, G.A.z, G.B1.z), z2 = __fmaf_rn(hz, G.A.z, G.B2.z);
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
+    const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -a2);
+    const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
+    *lb = l;
+    return !(l > ub);
 }
 
 // The exact gate: Box.intersect (division form) on the box of internal node g, as the reference evaluates it when it pops g.

@@ -585,6 +585,14 @@ inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 }  // namespace
 
 // ================================================= host side ==========================================================
+// where the tree kernel keeps the nodes of an n-leaf tree: in shared memory as packed 64-byte nodes, in shared memory as quantised
+// 32-byte nodes (trees up to twice as big), or in global memory (quantised)
+int ptb_tree_mode(const ptb_ctx* c, int n) {
+    if (c->no_resident_bvh) return PTB_TREE_GLOBAL;
+    if (!c->quant_resident_bvh && TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(n) <= (size_t)c->smem_optin) return PTB_TREE_RESIDENT;
+    if (TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(n) <= (size_t)c->smem_optin) return PTB_TREE_RESIDENT_QUANT;
+    return PTB_TREE_GLOBAL;
+}
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
 // which: 0 = extend, 1 = shadow / taps (selects the tree-queue counters of the control block, reset by k_ctrl_*)
 template <class IO>
@@ -603,14 +611,19 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
         if (c->counting) k_trace_pre<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
         else k_trace_pre<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
         // phase B: tree traversal of the survivors
-        const size_t resident = TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n);
-        if (resident <= (size_t)c->smem_optin && !c->no_resident_bvh) {
+        const int mode = ptb_tree_mode(c, S.n);
+        if (mode == PTB_TREE_RESIDENT) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
-            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true>;
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
-            kern<<<c->sm_count, PTB_TRACE_BLK_S, resident, st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n), st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
+        } else if (mode == PTB_TREE_RESIDENT_QUANT) {
+            // twice the size: resident as quantised 32-byte nodes
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(S.n), st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
         } else {
-            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false> : k_trace_tree<IO, false, PTB_TRACE_BLK, false>;
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK, false, true>;
             kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK>::fixed, st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
         }
         c->launches++;
@@ -665,6 +678,7 @@ int ptb_wf_init(ptb_ctx* c) {
     int occ = 0;
     PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
+    c->quant_resident_bvh = getenv("PTB_QUANT_RESIDENT_BVH") != nullptr;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
