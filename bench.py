@@ -198,7 +198,7 @@ def run_gpu(args):
     ctx.sobol_reset(); worker.clear()
     for _ in range(args.warmup):
         frame()
-    ctx.set_counting(False, True); ctx.reset_counters()
+    ctx.set_counting(False, False); ctx.reset_counters()
     sampler = ClockSampler(local); sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -210,7 +210,16 @@ def run_gpu(args):
     sampler.stop_flag = True
     sampler.join(timeout=10)      # an nvidia-smi query still in flight perturbs the host-synchronous e2e loop below
     ms = ev0.elapsed_time(ev1)
-    stage = ctx.stage_ms(); launches = ctx.launches()
+    launches = ctx.launches()
+    # per-stage device times: a separate pass with CUDA events around every stage.  It runs the stages one after the other; the
+    # timed region above overlaps the shadow stage of a bounce with the extend stage of the next one (two streams), where a
+    # per-kernel duration is not defined.
+    nprof = max(1, min(args.steps, 5))
+    ctx.set_counting(False, True); ctx.reset_counters()
+    for _ in range(nprof):
+        frame()
+    ctx.synchronize()
+    stage = ctx.stage_ms()
     ctx.set_counting(False, False)
     t = torch.tensor([ms], device='cuda')
     if world > 1:
@@ -278,7 +287,7 @@ def run_gpu(args):
         l2_gbs = ctx.measure_l2(64, 20)
         # dominant stage = BVH traversal (extend + shadow; each stage launch = k_trace_pre + k_trace_tree): algorithmic bytes per
         # launch = 64 B per node visit + 64 B per triangle test + 48 B per ray (32 B ray in, 16 B hit out)  -- DESIGN.md "Roofline"
-        n_trav_launches = 5 * args.steps * (2 if eng == _native.ENGINE_PATH else 1)
+        n_trav_launches = 5 * nprof * (2 if eng == _native.ENGINE_PATH else 1)
         ncu = {}
         try:    # DRAM bytes / issue-slot utilisation of the traversal kernels from the committed ncu capture of this build
             ncu = json.load(open(os.path.join(ROOT, 'profiles', 'traversal_ncu.json'))).get(sc['name'], {})
@@ -286,7 +295,7 @@ def run_gpu(args):
             pass
         trav_ms = stage['extend'] + stage['shadow']
         alg_bytes_step = 64.0 * cnt['node_visits'] + 64.0 * cnt['tri_tests'] + 48.0 * cnt['rays']
-        achieved = alg_bytes_step * args.steps / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        achieved = alg_bytes_step * nprof / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': config_of(sc, world),
@@ -298,11 +307,13 @@ def run_gpu(args):
                 'gpu_launches': int(launches),
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': (achieved / hbm_peak) if achieved else None, 'traffic': ncu.get('dram_bytes_per_launch'),
                              'kernel': 'k_trace_pre + k_trace_tree (BVH traversal: extend and shadow stages)', 'ncu': ncu or None, 'launches': n_trav_launches, 'avg_launch_ms': trav_ms / n_trav_launches,
-                             'algorithmic_bytes_per_launch': alg_bytes_step * args.steps / n_trav_launches, 'peak_source': peak_src,
+                             'algorithmic_bytes_per_launch': alg_bytes_step * nprof / n_trav_launches,
+                             'timing': f'CUDA events around every stage, serial pass of {nprof} steps after the timed region', 'peak_source': peak_src,
                              'l2_peak_gbs_measured': l2_gbs, 'frac_of_l2': (achieved / l2_gbs) if achieved else None,
                              'note': 'gather workload served from shared memory / L1 / L2 (the scene is cache resident): HBM is the schema bound; '
                                      'what binds is instruction issue (ncu: issue-slot utilisation, lanes per instruction -- profiles/)'},
-                'stage_ms_per_step': {k: v / args.steps for k, v in stage.items()},
+                'stage_ms_per_step': {k: v / nprof for k, v in stage.items()},
+                'schedule': 'shadow stage of bounce b overlapped with the extend stage of bounce b+1 (2 streams); stage_ms_per_step from a serial pass',
                 'counters_per_step_rank0': cnt,
                 'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms},
                 'clocks': sampler.summary()}

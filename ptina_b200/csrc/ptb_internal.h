@@ -121,6 +121,10 @@ struct ptb_ctx {
     RayQueue xq[2]{};               // extend queues (in / out, swapped every bounce)
     RayQueue sq{};                  // shadow queue
     ExpQ tq{};                      // tree queue
+    ExpQ tq2{};                     // second tree queue: the shadow stage of bounce b runs beside the extend stage of bounce b+1
+    cudaStream_t stream2 = nullptr; // non-blocking side stream of the shadow stage
+    cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
+    bool overlap_shadow = true;     // PTB_NO_OVERLAP=1 turns the overlap off
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
     int counting = 0;

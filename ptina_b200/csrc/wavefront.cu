@@ -128,6 +128,9 @@ __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, 
 
 __global__ void k_ctrl_begin(Ctrl* c, int n_in) { c->n_in = n_in; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; c->n_tree[0] = c->n_tree[1] = 0; c->cur_tree[0] = c->cur_tree[1] = 0; }
 __global__ void k_ctrl_tap(Ctrl* c, int m) { c->pad[0] = m; c->pad[1] = 0; c->n_tree[1] = 0; c->cur_tree[1] = 0; }
+// overlapped schedule: the shadow stage of the bounce still reads its own fields while the next extend stage is set up
+__global__ void k_ctrl_next_extend(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->cur_extend = 0; c->n_tree[0] = 0; c->cur_tree[0] = 0; }
+__global__ void k_ctrl_reset_shadow(Ctrl* c) { c->n_shadow = 0; c->cur_shadow = 0; c->n_tree[1] = 0; c->cur_tree[1] = 0; }
 __global__ void k_ctrl_next(Ctrl* c) { c->n_in = c->n_out; c->n_out = 0; c->n_shadow = 0; c->cur_extend = 0; c->cur_shadow = 0; c->n_tree[0] = c->n_tree[1] = 0; c->cur_tree[0] = c->cur_tree[1] = 0; }
 
 // ---- path.py:85-93 do_render (first half) / brute.py:66-73 -----------------------------------------------------------
@@ -596,9 +599,8 @@ int ptb_tree_mode(const ptb_ctx* c, int n) {
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
 // which: 0 = extend, 1 = shadow / taps (selects the tree-queue counters of the control block, reset by k_ctrl_*)
 template <class IO>
-static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int which, int* cursor, const int* count_ptr) {
+static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int which, int* cursor, const int* count_ptr, cudaStream_t st, const ExpQ& tq) {
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
-    cudaStream_t st = c->stream;
     if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
         if (c->counting) k_trace_simple<IO, 0, true><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
         else k_trace_simple<IO, 0, false><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
@@ -608,33 +610,33 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
     } else {
         int* n_tree = &c->d_ctrl->n_tree[which]; int* cur_tree = &c->d_ctrl->cur_tree[which];
         // phase A: per-ray setup, always-test list, root test; survivors -> tree queue
-        if (c->counting) k_trace_pre<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
-        else k_trace_pre<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, c->tq, n_tree, ctr);
+        if (c->counting) k_trace_pre<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, tq, n_tree, ctr);
+        else k_trace_pre<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, tq, n_tree, ctr);
         // phase B: tree traversal of the survivors
         const int mode = ptb_tree_mode(c, S.n);
         if (mode == PTB_TREE_RESIDENT) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
             auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
-            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n), st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else if (mode == PTB_TREE_RESIDENT_QUANT) {
             // twice the size: resident as quantised 32-byte nodes
             auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
-            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(S.n), st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
+            kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else {
             auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK, false, true>;
-            kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK>::fixed, st>>>(S, io, c->tq, cur_tree, n_tree, ctr);
+            kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK>::fixed, st>>>(S, io, tq, cur_tree, n_tree, ctr);
         }
         c->launches++;
     }
     c->launches++;
 }
 static void launch_extend(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
-    launch_trace_io(c, S, ExtendIO{q.o, q.d, c->st.hit}, policy, 0, cursor, count_ptr);
+    launch_trace_io(c, S, ExtendIO{q.o, q.d, c->st.hit}, policy, 0, cursor, count_ptr, c->stream, c->tq);
 }
-static void launch_shadow(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
-    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, 1, cursor, count_ptr);
+static void launch_shadow(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr, cudaStream_t st, const ExpQ& tq) {
+    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, 1, cursor, count_ptr, st, tq);
 }
 
 void ptb_stage_begin(ptb_ctx* c, int stage) {
@@ -667,7 +669,8 @@ int ptb_stage_collect(ptb_ctx* c) {
 int ptb_wf_init(ptb_ctx* c) {
     int64_t np = c->max_paths;
     float4** arrs[] = {&c->st.ray_o, &c->st.ray_d, &c->st.hit, &c->st.thr, &c->st.result,
-                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->tq.e[0], &c->tq.e[1], &c->tq.e[2], &c->tq.e[3], &c->tq.e[4]};
+                       &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->tq.e[0], &c->tq.e[1], &c->tq.e[2], &c->tq.e[3], &c->tq.e[4],
+                       &c->tq2.e[0], &c->tq2.e[1], &c->tq2.e[2], &c->tq2.e[3], &c->tq2.e[4]};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
     PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
     PTB_CUDA(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
@@ -679,6 +682,10 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
     c->quant_resident_bvh = getenv("PTB_QUANT_RESIDENT_BVH") != nullptr;
+    c->overlap_shadow = getenv("PTB_NO_OVERLAP") == nullptr;
+    PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
+    PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shadow, cudaEventDisableTiming));
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
@@ -723,24 +730,42 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     cudaStream_t st = c->stream;
     int cur = 0;
+    // The shadow stage of bounce b and the extend stage of bounce b+1 are independent (shadow rays add into `result`, which extend
+    // never touches; shade of b+1 waits for both), so they run on two streams: each fills the SMs the other leaves idle while its
+    // persistent kernels drain.  The per-path order of the additions into `result` is unchanged.  Off while stages are being timed.
+    const bool overlap = ENGINE == PTB_ENGINE_PATH && c->overlap_shadow && !c->profiling;
     for (int depth = 1; depth <= 5; depth++) {
         ptb_stage_begin(c, ST_EXTEND);
         launch_extend(c, S, policy, c->xq[cur], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
         ptb_stage_end(c);
+        if (overlap && depth > 1) {
+            PTB_CUDA(cudaStreamWaitEvent(st, c->ev_shadow, 0));           // the previous shadow stage is done with sq / result
+            k_ctrl_reset_shadow<<<1, 1, 0, st>>>(c->d_ctrl);
+            c->launches++;
+        }
         ptb_stage_begin(c, ST_SHADE);
         k_shade<ENGINE><<<c->sm_count * (1024 / SBLK), SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
                                                             c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
         ptb_stage_end(c);
         c->launches += 1;
         if (ENGINE == PTB_ENGINE_PATH) {
-            ptb_stage_begin(c, ST_SHADOW);
-            launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow);
-            ptb_stage_end(c);
+            if (overlap) {
+                PTB_CUDA(cudaEventRecord(c->ev_shade, st));
+                PTB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_shade, 0));
+                launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow, c->stream2, c->tq2);
+                PTB_CUDA(cudaEventRecord(c->ev_shadow, c->stream2));
+            } else {
+                ptb_stage_begin(c, ST_SHADOW);
+                launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow, st, c->tq);
+                ptb_stage_end(c);
+            }
         }
-        k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
+        if (overlap) k_ctrl_next_extend<<<1, 1, 0, st>>>(c->d_ctrl);
+        else k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
         c->launches++;
         cur ^= 1;
     }
+    if (overlap) PTB_CUDA(cudaStreamWaitEvent(st, c->ev_shadow, 0));
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -844,8 +869,8 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
     c->launches += 2;
     int eff = ptb_effective_policy(c, policy);
     int* cur = &c->d_ctrl->pad[1]; const int* cnt = &c->d_ctrl->pad[0];
-    if (anyhit) launch_trace_io(c, S, TapIO<true>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt);
-    else launch_trace_io(c, S, TapIO<false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt);
+    if (anyhit) launch_trace_io(c, S, TapIO<true>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq);
+    else launch_trace_io(c, S, TapIO<false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq);
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
