@@ -503,6 +503,23 @@ def test_batching_and_ranges_are_equivalent(gpu):
     assert np.allclose(a, c, rtol=1e-5, atol=1e-6) and np.array_equal(a[..., 3], c[..., 3])
 
 
+@pytest.mark.parametrize('name', ['cornell_monkey', 'mega_small'])
+def test_overlapped_schedule_is_bit_identical_to_serial(gpu, name):
+    """The production schedule runs the shadow stage of a bounce beside the extend stage of the next one (two streams); with
+    per-stage timing on, the stages run one after the other.  Same additions in the same order per path: identical films."""
+    sc, o = load(gpu, name, SMALL[name], ref=False)
+    gpu.render(_native.ENGINE_PATH, 8)
+    a = gpu.get_film().copy()
+    gpu.sobol_reset(); worker.clear()
+    gpu.set_counting(False, True)            # profiling: serial schedule
+    try:
+        gpu.render(_native.ENGINE_PATH, 8)
+        b = gpu.get_film().copy()
+    finally:
+        gpu.set_counting(False, False)
+    assert np.array_equal(bits(a), bits(b)) and a[..., 3].max() == 8
+
+
 def test_full_size_ordered_equals_reference_order(gpu):
     """BASELINE configs 1/2 at full 512x512: hit ids / depth / uv of the optimised traversal equal the literal reference
     traversal run on the GPU, for primary rays of several Sobol points (size-independent property)."""
