@@ -150,6 +150,37 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO
     flush_counters<COUNT>(C, nrays, IO::kAnyHit, ctr);
 }
 
+// ---- the always-test list (shared-memory copy: slots, packed triangles, gate boxes) ------------------------------------------------
+// The reference tests a listed triangle only if its gate passes Box.intersect (conservative test, exact when the ray grazes the gate).
+PTB_D bool list_gate_ok(const TraceScene& S, const float4 (*s_gate)[2], int j, int slot, const RayCons& R, V3 ro, V3 rd) {
+    const float4 glo = s_gate[j][0], ghi = s_gate[j][1];
+    float gl; bool gsure;
+    return slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], ro, rd));
+}
+// One pass over the list: closest accepted triangle (ties: larger slot) into ret / best; ANYHIT: stop at the first one.  GATED = false
+// leaves the gates out: the winner of the ungated pass is the winner of the gated one whenever its own gate passes (it is the
+// minimum over a superset), which the caller checks once per ray instead of once per candidate -- the gates of listed triangles are
+// boxes near the root, so the gated pass is a rare second pass.  *jw = list index of the winner.
+template <bool ANYHIT, bool GATED, bool COUNT>
+PTB_D bool list_scan(const TraceScene& S, const int* s_slot, const float4 (*s_tri)[4], const float4 (*s_gate)[2], int nlist, const RayIn& in, const RayCons& R,
+                     HitRec& ret, float& best, int* jw, TraceCounters& C) {
+    for (int j = 0; j < nlist; j++) {
+        const int slot = s_slot[j];
+        if (slot == in.avoid_slot) continue;
+        Tri64 T; T.a = s_tri[j][0]; T.b = s_tri[j][1]; T.c = s_tri[j][2]; T.d = s_tri[j][3];
+        if (COUNT) C.tris++;
+        float dep, s, t;
+        if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
+            const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
+            if (better && (!GATED || list_gate_ok(S, s_gate, j, slot, R, in.ro, in.rd))) {
+                ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep; *jw = j;
+                if (ANYHIT) return true;
+            }
+        }
+    }
+    return false;
+}
+
 // ---- production phase A: per-ray setup, always-test list, root test; survivors go to the tree queue ---------------------------------
 template <class IO, bool COUNT>
 __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const int* count_ptr, ExpQ xq, int* tree_count, DevCounters* ctr) {
@@ -196,25 +227,14 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
             } else {
                 R = ray_cons(in.ro, in.rd);
                 float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
-                bool occluded = false;
-                for (int j = 0; j < nlist; j++) {
-                    const int slot = s_slot[j];
-                    if (slot == in.avoid_slot) continue;
-                    Tri64 T; T.a = s_tri[j][0]; T.b = s_tri[j][1]; T.c = s_tri[j][2]; T.d = s_tri[j][3];
-                    if (COUNT) C.tris++;
-                    float dep, s, t;
-                    if (tri_fast(T, in.ro, in.rd, best, &dep, &s, &t)) {
-                        const bool better = ANYHIT ? dep < PTB_INF : (dep < ret.depth || (ret.hit && slot > ret.slot));
-                        if (better) {
-                            // the reference tests this triangle only if its gate passes Box.intersect: conservative, exact when grazing
-                            const float4 glo = s_gate[j][0], ghi = s_gate[j][1];
-                            float gl; bool gsure;
-                            if (slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], in.ro, in.rd))) {
-                                ret.depth = dep; ret.u = s; ret.v = t; ret.hit = 1; ret.slot = slot; best = dep;
-                                if (ANYHIT) { occluded = true; break; }
-                            }
-                        }
-                    }
+                const float best0 = best;
+                int jw = -1;
+                bool occluded = list_scan<ANYHIT, false, COUNT>(S, s_slot, s_tri, s_gate, nlist, in, R, ret, best, &jw, C);
+                if (ret.hit && !list_gate_ok(S, s_gate, jw, ret.slot, R, in.ro, in.rd)) {
+                    // the ungated winner is not a triangle the reference would have tested: start over, gate checked per candidate
+                    ret.hit = 0; ret.depth = PTB_INF; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1; best = best0;
+                    TraceCounters unused; unused.nodes = unused.boxes = unused.tris = 0; unused.max_stack = 0;
+                    occluded = list_scan<ANYHIT, true, false>(S, s_slot, s_tri, s_gate, nlist, in, R, ret, best, &jw, unused);
                 }
                 // anything left in the tree?  its root box = union of the inflated bounds of every triangle not in the list
                 if (!occluded && S.n >= 2) {
