@@ -13,7 +13,7 @@ void ptb_set_error(const char* fmt, ...) {
 
 TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
-    S.nodes = c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.nlo = c->d_nlo; S.nhi = c->d_nhi; S.list = c->d_list; S.nlist = c->list_n; S.scene_abs = c->scene_abs; S.root_must = c->root_must; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
+    S.nodes = c->d_nodes_active ? c->d_nodes_active : c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.nlo = c->d_nlo; S.nhi = c->d_nhi; S.list = c->d_list; S.nlist = c->list_n; S.scene_abs = c->scene_abs; S.root_must = c->root_must; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
     S.qnodes = c->d_qnodes;
     for (int k = 0; k < 3; k++) { S.qbase[k] = c->qbase[k]; S.qext[k] = c->qext[k]; S.qinv[k] = c->qinv[k]; }
     return S;
@@ -113,7 +113,8 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
         dmalloc(&c->d_mc, nf) || dmalloc(&c->d_id, nf) || dmalloc(&c->d_mc_tmp, nf) || dmalloc(&c->d_id_tmp, nf) || dmalloc(&c->d_leaf, nf) ||
         dmalloc(&c->d_child, nf) || dmalloc(&c->d_bmin, nf * 3) || dmalloc(&c->d_bmax, nf * 3) || dmalloc(&c->d_ready, nf) ||
         dmalloc(&c->d_parentcnt, nf * 2) || dmalloc(&c->d_range, nf) || dmalloc(&c->d_height, nf) || dmalloc(&c->d_nodes, nf) || dmalloc(&c->d_qnodes, 2 * nf) ||
-        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_slot_of, nf) || dmalloc(&c->d_gate, nf) || dmalloc(&c->d_gbox, 2 * nf) || dmalloc(&c->d_tlo, nf) || dmalloc(&c->d_thi, nf) || dmalloc(&c->d_nlo, nf) || dmalloc(&c->d_nhi, nf) || dmalloc(&c->d_list, PTB_LIST_CAP) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
+        dmalloc(&c->d_tris, nf) || dmalloc(&c->d_slot_of, nf) || dmalloc(&c->d_gate, nf) || dmalloc(&c->d_gbox, 2 * nf) || dmalloc(&c->d_tlo, nf) || dmalloc(&c->d_thi, nf) || dmalloc(&c->d_nlo, nf) || dmalloc(&c->d_nhi, nf) || dmalloc(&c->d_list, PTB_LIST_CAP) || dmalloc(&c->d_nodes2, 8200) || dmalloc(&c->d_pl_id[0], 8200) || dmalloc(&c->d_pl_id[1], 8200) || dmalloc(&c->d_pl_depth[0], 8200) || dmalloc(&c->d_pl_depth[1], 8200) || dmalloc(&c->d_pl_nn, 8200) ||
+        dmalloc(&c->d_pl_lo[0], 8200) || dmalloc(&c->d_pl_lo[1], 8200) || dmalloc(&c->d_pl_hi[0], 8200) || dmalloc(&c->d_pl_hi[1], 8200) || dmalloc(&c->d_scalars, 64) || dmalloc(&c->d_film, (size_t)d.max_filmsize * d.max_filmpasses)) {
         delete c; return 1;
     }
     PTB_CUDA(cudaMemset(c->d_film, 0, sizeof(float4) * (size_t)d.max_filmsize * d.max_filmpasses));
@@ -136,7 +137,7 @@ int ptb_destroy(ptb_ctx* c) {
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_cache, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
-                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_qnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_nodes2, c->d_pl_id[0], c->d_pl_id[1], c->d_pl_depth[0], c->d_pl_depth[1], c->d_pl_nn, c->d_pl_lo[0], c->d_pl_lo[1], c->d_pl_hi[0], c->d_pl_hi[1], c->d_qnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
                     c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->tq.e[0], c->tq.e[1], c->tq.e[2], c->tq.e[3], c->tq.e[4], c->tq2.e[0], c->tq2.e[1], c->tq2.e[2], c->tq2.e[3], c->tq2.e[4],
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold, c->d_resolve};
     for (void* p : ptrs) if (p) cudaFree(p);

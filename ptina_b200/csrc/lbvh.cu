@@ -31,11 +31,11 @@ __device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int f
 }
 
 // scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height,
-// [11] always-test list length, [12] list overflow, [13] sweeps, [14] node planes outside the quantisation grid
+// [11] always-test list length, [12] list overflow, [13] sweeps, [14] node planes outside the quantisation grid, [15] height of the PLOC traversal tree
 __global__ void k_init_scalars(float* s) {
     s[0] = s[1] = s[2] = PTB_INF;
     s[3] = s[4] = s[5] = -PTB_INF;
-    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0; ((int*)s)[13] = 0; ((int*)s)[14] = 0;
+    ((int*)s)[8] = 0; ((int*)s)[9] = 0; ((int*)s)[10] = 0; ((int*)s)[11] = 0; ((int*)s)[12] = 0; ((int*)s)[13] = 0; ((int*)s)[14] = 0; ((int*)s)[15] = -1;
 }
 
 // lbvh.py:172-176: bounds of the triangle CENTRES (atomic min/max; exact, order-free)
@@ -378,6 +378,118 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const int2* __restrict__ chi
     nodes[i] = N;
 }
 
+// ---- a better traversal tree for small scenes: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) ---------------------
+// The traversal tree only has to be conservative (ptb_traverse.cuh): any binary tree over the unlisted triangles whose node boxes
+// contain the inflated bounds below them gives the reference's answer once the winner's gate is checked.  The LBVH topology splits at
+// the spatial medians of the whole scene; PLOC merges, bottom-up along the Morton order the slots already have, every pair of clusters
+// that are each other's nearest neighbour (smallest surface area of the union, search radius PTB_PLOC_R) -- lower SAH cost, shallower.
+// One block (trees up to PTB_SMALL_TREE internal nodes); deterministic.  Nodes are numbered downward from m0 - 2 in creation order,
+// so the root (created last) is node 0.  scal[15] = height of the tree (-1: not built).
+#define PTB_PLOC_R 16
+struct PlocBufs { int* id[2]; float4* lo[2]; float4* hi[2]; int* depth[2]; int* nn; };
+__device__ __forceinline__ float ploc_cost(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+// exclusive scan over the block of one int per thread (two 16-bit counters packed); *total = sum
+__device__ __forceinline__ int ploc_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+__global__ void __launch_bounds__(1024) k_ploc_small(const float4* __restrict__ tlo, const float4* __restrict__ thi, const float4* __restrict__ gbox, int n,
+                                                     PlocBufs B, Node64* __restrict__ nodes, int* __restrict__ scal) {
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x;
+    // clusters = the unlisted, testable leaf slots, in slot (Morton) order; an ill-conditioned triangle is bounded by its gate box
+    int chunk = (n + 1023) / 1024, first = min(n, tid * chunk), last = min(n, first + chunk), cnt = 0, total;
+    for (int s = first; s < last; s++) cnt += (__float_as_int(tlo[s].w) & (PTB_TF_NEVER | PTB_TF_LISTED)) == 0;
+    int pos = ploc_scan(cnt, s_warp, &total);
+    for (int s = first; s < last; s++) {
+        const int fl = __float_as_int(tlo[s].w);
+        if (fl & (PTB_TF_NEVER | PTB_TF_LISTED)) continue;
+        const bool must = (fl & PTB_TF_MUST) != 0;
+        B.id[0][pos] = must ? (s | PTB_NODE_MUST) : s;
+        B.lo[0][pos] = must ? gbox[2 * s] : tlo[s];
+        B.hi[0][pos] = must ? gbox[2 * s + 1] : thi[s];
+        B.depth[0][pos] = 0;
+        pos++;
+    }
+    int m = total;
+    const int m0 = m;
+    if (m0 < 2) { if (tid == 0) scal[15] = -1; return; }
+    int created = 0, cur = 0;
+    __syncthreads();
+    while (m > 1) {
+        const int* id = B.id[cur]; const float4* lo = B.lo[cur]; const float4* hi = B.hi[cur]; const int* dep = B.depth[cur];
+        for (int i = tid; i < m; i += 1024) {
+            const float4 alo = lo[i], ahi = hi[i];
+            float best = 0.0f; int bj = -1;
+            const int j0 = max(0, i - PTB_PLOC_R), j1 = min(m - 1, i + PTB_PLOC_R);
+            for (int j = j0; j <= j1; j++) {
+                if (j == i) continue;
+                const float c = ploc_cost(alo, ahi, lo[j], hi[j]);
+                if (bj < 0 || c < best) { best = c; bj = j; }
+            }
+            B.nn[i] = bj;
+        }
+        __syncthreads();
+        // mutual nearest neighbours merge (the lower index keeps the slot); counts: clusters kept (low half), nodes created (high half)
+        chunk = (m + 1023) / 1024; first = min(m, tid * chunk); last = min(m, first + chunk); cnt = 0;
+        for (int i = first; i < last; i++) {
+            const int j = B.nn[i];
+            const bool mutual = B.nn[j] == i;
+            if (mutual && j < i) continue;
+            cnt += 1 + ((mutual && i < j) ? 0x10000 : 0);
+        }
+        const int excl = ploc_scan(cnt, s_warp, &total);
+        int kpos = excl & 0xffff, mpos = excl >> 16;
+        for (int i = first; i < last; i++) {
+            const int j = B.nn[i];
+            const bool mutual = B.nn[j] == i;
+            if (mutual && j < i) continue;
+            int cid = id[i], cdep = dep[i];
+            float4 clo = lo[i], chi = hi[i];
+            if (mutual) {
+                const int node = (m0 - 2) - (created + mpos++);
+                const float4 blo = lo[j], bhi = hi[j];
+                const int idj = id[j];
+                Node64 N;
+                N.a = make_float4(clo.x, clo.y, clo.z, __int_as_float(cid));
+                N.b = make_float4(chi.x, chi.y, chi.z, __int_as_float(idj));
+                N.c = make_float4(blo.x, blo.y, blo.z, 0.0f);
+                N.d = make_float4(bhi.x, bhi.y, bhi.z, 0.0f);
+                nodes[node] = N;
+                clo = make_float4(fminf(clo.x, blo.x), fminf(clo.y, blo.y), fminf(clo.z, blo.z), 0.0f);
+                chi = make_float4(fmaxf(chi.x, bhi.x), fmaxf(chi.y, bhi.y), fmaxf(chi.z, bhi.z), 0.0f);
+                cid = (n + node) | ((cid | idj) & PTB_NODE_MUST);
+                cdep = max(cdep, dep[j]) + 1;
+            }
+            B.id[cur ^ 1][kpos] = cid; B.lo[cur ^ 1][kpos] = clo; B.hi[cur ^ 1][kpos] = chi; B.depth[cur ^ 1][kpos] = cdep;
+            kpos++;
+        }
+        created += total >> 16;
+        m = total & 0xffff;
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (tid == 0) scal[15] = B.depth[cur][0];
+}
+
 // Node32 (ptb_traverse.cuh): the boxes of a packed node on the 15-bit grid, rounded outward.  The candidate from the f32 estimate is
 // corrected against the exact value of the plane it decodes to (base + (1 + q/32768) * ext: a 24-bit plus a 16-bit number of
 // nearby exponents, exact in double), so lo' <= lo and hi' >= hi hold as real numbers whatever the rounding of the estimate.
@@ -514,6 +626,14 @@ int ptb_lbvh_build(ptb_ctx* c) {
         else for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
         k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_bmin, c->d_bmax, n, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_nodes, c->d_gate, c->d_gbox);
         c->launches += small ? 5 : 4 + sweeps;
+        if (small && c->use_ploc) {
+            PlocBufs B;
+            for (int k = 0; k < 2; k++) { B.id[k] = c->d_pl_id[k]; B.lo[k] = c->d_pl_lo[k]; B.hi[k] = c->d_pl_hi[k]; B.depth[k] = c->d_pl_depth[k]; }
+            B.nn = c->d_pl_nn;
+            PTB_CUDA(cudaMemsetAsync(c->d_nodes2, 0xFF, sizeof(Node64) * (size_t)(n - 1), st));     // ids -1: slots PLOC leaves unused
+            k_ploc_small<<<1, 1024, 0, st>>>(c->d_tlo, c->d_thi, c->d_gbox, n, B, c->d_nodes2, c->d_scalars);
+            c->launches++;
+        }
     }
     if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }
     PTB_CUDA(cudaEventRecord(e1, st));
@@ -548,6 +668,9 @@ int ptb_lbvh_build(ptb_ctx* c) {
         c->list_n = n > 1 ? h_scal[11] : 0;
         c->list_overflow = n > 1 ? h_scal[12] : 0;
         for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
+        // the PLOC tree replaces the LBVH topology for traversal when it was built and fits the traversal stack
+        c->trav_depth = (n > 1 && n - 1 <= PTB_SMALL_TREE && c->use_ploc) ? h_scal[15] : -1;
+        c->d_nodes_active = (c->trav_depth >= 1 && c->trav_depth <= PTB_STACK) ? c->d_nodes2 : c->d_nodes;
         // quantised nodes for a tree too big to be resident as 64-byte nodes (wavefront.cu launch_trace_io decides the same way)
         if (valid && ptb_tree_mode(c, n) != PTB_TREE_RESIDENT) {
             QuantGrid g;
@@ -571,7 +694,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
             }
             int bad = 1;
             if (finite) {
-                k_quant_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_nodes, n, g, c->d_qnodes, c->d_scalars);
+                k_quant_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_nodes_active, n, g, c->d_qnodes, c->d_scalars);
                 c->launches++;
                 PTB_CUDA(cudaMemcpyAsync(&bad, &c->d_scalars[14], sizeof(int), cudaMemcpyDeviceToHost, st));
                 PTB_CUDA(cudaStreamSynchronize(st));

@@ -92,6 +92,11 @@ struct ptb_ctx {
     int2* d_range = nullptr;        // (min slot, max slot) per internal node
     int32_t* d_height = nullptr;
     Node64* d_nodes = nullptr;
+    Node64* d_nodes2 = nullptr;     // PLOC traversal tree of small scenes (lbvh.cu k_ploc_small); d_nodes_active = the one traversed
+    Node64* d_nodes_active = nullptr;
+    int *d_pl_id[2]{}, *d_pl_depth[2]{}, *d_pl_nn = nullptr; float4 *d_pl_lo[2]{}, *d_pl_hi[2]{};   // PLOC cluster buffers
+    bool use_ploc = true;           // PTB_NO_PLOC=1: keep the LBVH topology for traversal
+    int trav_depth = -1;
     uint4* d_qnodes = nullptr;      // [2(n-1)] quantised copy of d_nodes (Node32), built for trees that are traversed out of global memory
     float qbase[3]{}, qext[3]{1.0f, 1.0f, 1.0f}, qinv[3]{1.0f, 1.0f, 1.0f};
     Tri64* d_tris = nullptr;

@@ -683,6 +683,7 @@ int ptb_wf_init(ptb_ctx* c) {
     c->no_resident_bvh = getenv("PTB_NO_RESIDENT_BVH") != nullptr;
     c->quant_resident_bvh = getenv("PTB_QUANT_RESIDENT_BVH") != nullptr;
     c->overlap_shadow = getenv("PTB_NO_OVERLAP") == nullptr;
+    c->use_ploc = getenv("PTB_NO_PLOC") == nullptr;
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shadow, cudaEventDisableTiming));
