@@ -385,7 +385,9 @@ __global__ void __launch_bounds__(BLK) k_pack_nodes(const int2* __restrict__ chi
 // that are each other's nearest neighbour (smallest surface area of the union, search radius PTB_PLOC_R) -- lower SAH cost, shallower.
 // One block (trees up to PTB_SMALL_TREE internal nodes); deterministic.  Nodes are numbered downward from m0 - 2 in creation order,
 // so the root (created last) is node 0.  scal[15] = height of the tree (-1: not built).
-#define PTB_PLOC_R 16
+#ifndef PTB_PLOC_R
+#define PTB_PLOC_R 8           /* search radius along the Morton order: 16 builds the same trees here, 32 slightly better ones for a slower build */
+#endif
 struct PlocBufs { int* id[2]; float4* lo[2]; float4* hi[2]; int* depth[2]; int* nn; };
 __device__ __forceinline__ float ploc_cost(float4 alo, float4 ahi, float4 blo, float4 bhi) {
     const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
