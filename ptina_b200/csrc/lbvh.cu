@@ -236,6 +236,9 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
 // inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> the leaf is bounded by its GATE box instead, the
 // reference box of its parent, which any accepted triangle's ray must pass anyway), 4 = BIG (bounds cover more than 1/16 of the
 // scene's box area: hurts every ancestor's box -> always-test list if there is room).
+#ifndef PTB_BIG_FRACTION
+#define PTB_BIG_FRACTION (1.0f / 4.0f)      /* a triangle is BIG when its box surface exceeds this fraction of the scene's (walls: 1/3) */
+#endif
 #define PTB_TF_NEVER 1
 #define PTB_TF_MUST 2
 #define PTB_TF_BIG 4
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(BLK) k_tri_prep(const float* __restrict__ vert
         // scene extent = extent of the triangle centres (lbvh.py:172-176), the only bounds known before the boxes are built
         V3 e = mk3(scal[3] - scal[0], scal[4] - scal[1], scal[5] - scal[2]), d = hi - lo;
         float scene = e.x * e.y + e.y * e.z + e.z * e.x, own = d.x * d.y + d.y * d.z + d.z * d.x;
-        if (own > scene * (1.0f / 16.0f)) flags |= PTB_TF_BIG;
+        if (own > scene * PTB_BIG_FRACTION) flags |= PTB_TF_BIG;
     }
     tlo[s] = make_float4(__fadd_rd(lo.x, -eps), __fadd_rd(lo.y, -eps), __fadd_rd(lo.z, -eps), __int_as_float(flags));
     thi[s] = make_float4(__fadd_ru(hi.x, eps), __fadd_ru(hi.y, eps), __fadd_ru(hi.z, eps), 0.0f);

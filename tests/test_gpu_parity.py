@@ -41,7 +41,7 @@ def test_lbvh_bit_exact(gpu, name):
     for key in ('bmin', 'bmax'):
         assert np.array_equal(bits(a[key]), bits(b[key])), f'{name}: {key} differs'
     assert info.valid == 1 and info.depth == o.validate_tree() and info.policy == _native.TRAVERSE_ORDERED
-    assert info.list_overflow == 0 and info.list_n == {'cornell_boxes': 18, 'cornell_monkey': 10}.get(name, info.list_n)
+    assert info.list_overflow == 0 and info.list_n == {'cornell_boxes': 10, 'cornell_monkey': 10}.get(name, info.list_n)
 
 
 @pytest.mark.parametrize('name', list(SMALL))
@@ -217,7 +217,7 @@ def _soup(rng, kind):
     c = rng.uniform(-1, 1, (60, 3)) * 0.7 + 6.0; add(c, rng.normal(size=(60, 3)) * 1e-3, rng.normal(size=(60, 3)) * 1e-3)   # tiny, off-centre
     nbig = {'few_big': 6, 'many_big': 50, 'no_big': 0}[kind]
     if nbig:
-        c = rng.uniform(-1.2, -0.8, (nbig, 3)); add(c, rng.uniform(1.5, 2.5, (nbig, 3)), rng.uniform(1.5, 2.5, (nbig, 3)) * [1, -1, 1])
+        c = rng.uniform(-1.2, -0.8, (nbig, 3)); add(c, rng.uniform(4.5, 6.5, (nbig, 3)), rng.uniform(4.5, 6.5, (nbig, 3)) * [1, -1, 1])
     t = np.concatenate(tris, 0).astype(np.float32)
     t = np.concatenate([t, t[:12]], 0)                                                                            # exact duplicates
     n = t.shape[0]
