@@ -110,6 +110,12 @@ int ptb_set_traversal(ptb_ctx* ctx, int policy);
 /* tap: the reference's own arrays (lbvh.py:50-59); any pointer may be NULL.  mc,id,leaf [n]; child [n-1][2];
  * bmin,bmax [n-1][3] */
 int ptb_export_tree(ptb_ctx* ctx, int32_t* mc, int32_t* id, int32_t* child, int32_t* leaf, float* bmin, float* bmax);
+/* tap: the production traversal structure (no counterpart in the reference; tests validate it).  nodes [n-1][16]: per internal
+ * node the boxes of its two children and their ids -- (lo0.xyz, id0) (hi0.xyz, id1) (lo1.xyz, -) (hi1.xyz, -); id: -1 nothing
+ * below, bit 30 = exempt from distance culling, low bits < n = leaf slot, otherwise n + internal index; root = node 0; unused
+ * entries have both ids -1.  leaf_lo/leaf_hi [n][4]: inflated bounds per leaf slot (lo.w = flags: 1 never hit, 2 ill-conditioned,
+ * 4 big, 8 on the always-test list).  gbox [2n][4]: reference box of each slot's gate.  ploc: 1 = PLOC topology, 0 = LBVH's. */
+int ptb_export_traversal(ptb_ctx* ctx, float* nodes, float* leaf_lo, float* leaf_hi, float* gbox, int32_t* ploc);
 
 /* filmtable.py:41-45 */
 int ptb_set_size(ptb_ctx* ctx, int nx, int ny);

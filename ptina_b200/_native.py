@@ -45,7 +45,7 @@ SYMBOLS = [
     'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_synchronize',
     'ptb_set_sobol_table', 'ptb_sobol_reset', 'ptb_sobol_get_time', 'ptb_sobol_set_time', 'ptb_sobol_point',
     'ptb_load_model', 'ptb_load_materials', 'ptb_load_images', 'ptb_clear_lights', 'ptb_add_light', 'ptb_set_world_light',
-    'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
+    'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_export_traversal', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
     'ptb_film_ptr', 'ptb_render', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_mlt_state', 'ptb_get_image',
     'ptb_fast_export_image', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
     'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_render_sample',
@@ -232,6 +232,15 @@ class Context:
         child, bmin, bmax = np.zeros((m, 2), np.int32), np.zeros((m, 3), np.float32), np.zeros((m, 3), np.float32)
         self._check(self.L.ptb_export_tree(self.h, _ptr(mc), _ptr(id_), _ptr(child), _ptr(leaf), _ptr(bmin), _ptr(bmax)))
         return dict(mc=mc, id=id_, child=child, leaf=leaf, bmin=bmin, bmax=bmax)
+
+    def export_traversal(self):
+        """The production traversal structure (include/ptina_b200.h ptb_export_traversal)."""
+        n = self.nfaces
+        nodes = np.zeros((max(n - 1, 0), 16), np.float32)
+        lo, hi, gbox = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((2 * n, 4), np.float32)
+        ploc = ctypes.c_int32()
+        self._check(self.L.ptb_export_traversal(self.h, _ptr(nodes), _ptr(lo), _ptr(hi), _ptr(gbox), ctypes.byref(ploc)))
+        return dict(nodes=nodes, leaf_lo=lo, leaf_hi=hi, gbox=gbox, ploc=bool(ploc.value))
 
     # ---- film ------------------------------------------------------------------------------------
     def set_size(self, nx, ny):

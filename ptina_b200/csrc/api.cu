@@ -280,6 +280,22 @@ int ptb_export_tree(ptb_ctx* c, int32_t* mc, int32_t* id, int32_t* child, int32_
     return 0;
 }
 
+int ptb_export_traversal(ptb_ctx* c, float* nodes, float* leaf_lo, float* leaf_hi, float* gbox, int32_t* ploc) {
+    CHECK_CTX(c);
+    DeviceGuard g(c->device);
+    const int n = c->tree_n;
+    if (n < 2) { ptb_set_error("no traversal structure (fewer than 2 faces)"); return 1; }
+    cudaStream_t s = c->stream;
+    const Node64* src = c->d_nodes_active ? c->d_nodes_active : c->d_nodes;
+    if (nodes) PTB_CUDA(cudaMemcpyAsync(nodes, src, sizeof(Node64) * (size_t)(n - 1), cudaMemcpyDeviceToHost, s));
+    if (leaf_lo) PTB_CUDA(cudaMemcpyAsync(leaf_lo, c->d_tlo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (leaf_hi) PTB_CUDA(cudaMemcpyAsync(leaf_hi, c->d_thi, 16 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (gbox) PTB_CUDA(cudaMemcpyAsync(gbox, c->d_gbox, 32 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    PTB_CUDA(cudaStreamSynchronize(s));
+    if (ploc) *ploc = c->d_nodes_active == c->d_nodes2;
+    return 0;
+}
+
 // ---- film ------------------------------------------------------------------------------------------------------------
 int ptb_set_size(ptb_ctx* c, int nx, int ny) {
     CHECK_CTX(c);

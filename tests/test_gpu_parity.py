@@ -88,6 +88,62 @@ def test_secondary_rays_match_reference_order(gpu, name):
         assert np.array_equal(gpu.occluded(rays, dis, avoid, policy), want)
 
 
+@pytest.mark.parametrize('name', ['cornell_boxes', 'cornell_monkey', 'matball', 'mega_small'])
+def test_traversal_structure_is_a_conservative_tree(gpu, name):
+    """The structure the production kernel walks (PLOC topology for small scenes, the LBVH's for big ones): a proper binary tree
+    from node 0 in which every triangle that is neither listed nor untestable is a leaf exactly once, every stored child box is
+    the exact union of what is below it, leaf boxes are the inflated bounds (the gate box for ill-conditioned triangles, which
+    carry the no-distance-cull flag up to the root), and the height fits the traversal stack."""
+    sc, o = load(gpu, name, SMALL[name], ref=False)
+    t = gpu.export_traversal()
+    n = t['leaf_lo'].shape[0]
+    assert t['ploc'] == (n - 1 <= 8192)
+    nodes = t['nodes']
+    ids = np.stack([nodes[:, 3].view(np.int32), nodes[:, 7].view(np.int32)], 1)
+    lo = np.stack([nodes[:, 0:3], nodes[:, 8:11]], 1); hi = np.stack([nodes[:, 4:7], nodes[:, 12:15]], 1)
+    flags = t['leaf_lo'][:, 3].view(np.int32)
+    seen = np.zeros(n, np.int32)
+    visited = np.zeros(n - 1, bool)
+    # iterative post-order: box and must-flag of every internal node from its stored child entries
+    box_lo, box_hi, must_of, height = {}, {}, {}, {}
+    stack = [(0, False)]
+    while stack:
+        j, done = stack.pop()
+        if not done:
+            assert not visited[j], 'node reached twice'
+            visited[j] = True
+            stack.append((j, True))
+            for k in range(2):
+                c = ids[j, k]
+                if c >= 0 and (c & 0x3FFFFFFF) >= n:
+                    stack.append(((c & 0x3FFFFFFF) - n, False))
+            continue
+        l, h, m, ht = [], [], False, 1
+        for k in range(2):
+            c = ids[j, k]
+            if c < 0:
+                continue
+            cm, c = bool(c & 0x40000000), c & 0x3FFFFFFF
+            if c < n:
+                seen[c] += 1
+                assert (flags[c] & (1 | 8)) == 0, 'a listed / untestable triangle is in the tree'
+                is_must = bool(flags[c] & 2)
+                want_lo, want_hi = (t['gbox'][2 * c, :3], t['gbox'][2 * c + 1, :3]) if is_must else (t['leaf_lo'][c, :3], t['leaf_hi'][c, :3])
+                assert cm == is_must
+            else:
+                want_lo, want_hi, is_must = box_lo[c - n], box_hi[c - n], must_of[c - n]
+                assert cm == is_must
+                ht = max(ht, 1 + height[c - n])
+            assert np.array_equal(lo[j, k], want_lo) and np.array_equal(hi[j, k], want_hi)
+            l.append(lo[j, k]); h.append(hi[j, k]); m = m or cm
+        assert l, 'internal node with nothing below it is referenced'
+        box_lo[j], box_hi[j], must_of[j], height[j] = np.min(l, 0), np.max(h, 0), m, ht
+    active = (flags & (1 | 8)) == 0
+    assert np.array_equal(seen, active.astype(np.int32))
+    assert height[0] <= 64
+    assert np.all(ids[~visited] == -1) or not t['ploc']          # PLOC: entries it did not use are marked empty
+
+
 @pytest.mark.parametrize('name', ['cornell_monkey', 'mega_small'])
 def test_literal_traversal_work_counts_equal_the_oracle(gpu, name):
     """Integer parity of the work itself: under the literal policy (lbvh.py:313-347) the GPU pops, box-tests and triangle-tests
