@@ -1,12 +1,21 @@
-"""bench.py -- headline benchmark: PathEngine on the Cornell+monkey scene (BASELINE.json configs[1]:
-978 triangles, 512x512, 32 spp, LBVH + MIS area light), metric Mrays/s (extend + shadow rays traced per second).
+"""bench.py -- headline benchmark: PathEngine on the Cornell+monkey scene (BASELINE.json configs[1]: 978 triangles, 512x512,
+32 spp, LBVH + MIS area light), metric Mrays/s (extend + shadow rays traced per second), plus a `configs` block with every
+BASELINE config at the run's GPU count.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scene NAME]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scene NAME] [--quick]
 
-A step = one full frame: `spp` calls of PathEngine.render() on one GPU (N GPUs: every rank renders `spp` samples of the
-same frame at rank-interleaved Sobol indices -> weak scaling, film combined with one NCCL reduce per step).
-`value` times steps with the scene resident in HBM; `e2e` times the whole user-visible call sequence from pinned host
-buffers: load_model (H2D) + build_tree + render + get_image (D2H).
+Headline (`value`, `e2e`, `roofline`): a step = one full frame on every GPU -- rank g renders `spp` samples of the frame at
+rank-interleaved Sobol indices (weak scaling), and for N > 1 the films are summed onto rank 0 with one NCCL reduce per step.
+  value        steps timed on the device (CUDA events), scene resident in HBM
+  e2e          the user-visible call sequence from pinned host buffers each step: ModelPool.load (H2D) + BVHTree.build +
+               FilmTable.clear + render + FilmTable.get_image (D2H)
+  e2e_percall  the same sequence with the reference's own call pattern -- 32 x PathEngine().render(), one sample per call
+               (exams/benchmark.py:29-33); the library records the calls and submits them as one batch
+  sustained    the same step repeated for >= 2 s (clocks under sustained load)
+`configs`: config 1 (34 triangles), 2, 3 (BruteEngine 1024x1024, textures + environment), 4 (1.02 M triangles, 1920x1080: a fixed
+  32-spp step SHARDED over the N GPUs + the 33 MB film reduce, and the full 1024-spp render), 5 (MLT, 2^18 chains sharded over the
+  N GPUs), the strong-scaling split of a config-2 frame, and for N > 1 `film_check` (reduced film vs a 1-GPU render of the same
+  Sobol indices) and what limits each sharded config (kernel tails vs reduce vs host enqueue), with numbers.
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
 """
 import argparse
@@ -34,27 +43,29 @@ def parse():
     ap.add_argument('--spp', type=int, default=0)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='headline only: no configs block, no sustained window')
+    ap.add_argument('--one-step', action='store_true', help='profiling aid: set up, then exactly one step between cudaProfilerStart/Stop')
     return ap.parse_args()
 
 
-def workload(args):
+STEP_SPP = {'cornell_boxes': 32, 'cornell_monkey': 32, 'matball': 32, 'mega': 32}
+
+
+def workload(args, name=None):
     from ptina_b200 import scenes
-    sc = scenes.CONFIGS[args.scene]()
-    if args.spp:
-        sc['spp'] = args.spp
-    if args.scene == 'mega' and not args.spp:
-        sc['spp'] = 4          # a bench step of config 4 is 4 spp at 1080p (1024 spp is the quality target, not a step)
-    if args.scene == 'matball' and not args.spp:
-        sc['spp'] = 16
+    name = name or args.scene
+    sc = scenes.CONFIGS[name]()
+    sc['spp'] = args.spp if (args.spp and name == args.scene) else STEP_SPP.get(name, sc['spp'])
     return sc
 
 
-def config_of(sc, n_gpus):
+def config_of(sc, n_gpus, mode='weak'):
     nx, ny = sc['size']
-    return {'workload': f"{sc['name']}: {len(sc['mtlids'])} tris, {nx}x{ny}, {sc['spp']} spp/step/GPU, engine={sc['engine']}",
+    per = f"{sc['spp']} spp/step/GPU" if mode == 'weak' else f"{sc['spp']} spp/step split over the GPUs"
+    return {'workload': f"{sc['name']}: {len(sc['mtlids'])} tris, {nx}x{ny}, {per}, engine={sc['engine']}",
             'scene': sc['name'], 'tris': int(len(sc['mtlids'])), 'resolution': [nx, ny], 'spp_per_step_per_gpu': sc['spp'],
             'parallelism': f'sample-range x{n_gpus}' if n_gpus > 1 else 'single GPU',
-            'l2_policy': 'path state per step (>=0.9 GB) exceeds the 126 MB L2, so every step starts cold'}
+            'l2_policy': 'path state and ray queues of a step (>= 0.9 GB) exceed the 126 MB L2, so every step starts cold'}
 
 
 class ClockSampler(threading.Thread):
@@ -101,6 +112,11 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.1)
+
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=10)
+        return self.summary()
 
     def summary(self):
         if not self.samples:
@@ -154,83 +170,278 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# =====================================================================================================================
+class Bench:
+    """One process = one GPU.  Holds the distributed plumbing and the measurement primitives shared by every config."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank, self.world, self.local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+        from ptina_b200 import scenes, worker, _native
+        from ptina_b200 import dist as pdist
+        self.scenes, self.worker, self.native, self.pdist = scenes, worker, _native, pdist
+        worker.init(device=self.local)
+        self.ctx = _native.context()
+        self.current = None
+
+    # ---- plumbing ----
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device='cuda', dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device='cuda', dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def load(self, sc):
+        if self.current != sc['name']:
+            self.scenes.apply(self.worker, sc)
+            self.current = sc['name']
+        self.ctx.sobol_reset()
+        self.worker.clear()
+        return {'path': self.native.ENGINE_PATH, 'brute': self.native.ENGINE_BRUTE, 'mlt': self.native.ENGINE_MLT}[sc['engine']]
+
+    # ---- one path-traced step: `total` Sobol indices from the generator's time on, interleaved over the ranks, + film reduce ----
+    def make_frame(self, eng, total, reduce=True):
+        ctx, pdist, rank, world = self.ctx, self.pdist, self.rank, self.world
+
+        def frame():
+            k0 = ctx.sobol_time + 1
+            first, count, stride = pdist.shard_range(k0, total, rank, world)
+            if count:
+                ctx.render_range(eng, first, count, stride)
+            ctx.sobol_time = ctx.sobol_time + total
+            if world > 1 and reduce:
+                return pdist.reduce_film_pass(0, 0)
+            return None
+        return frame
+
+    def count_rays(self, frame):
+        ctx = self.ctx
+        ctx.sobol_reset(); self.worker.clear()
+        ctx.set_counting(True, False); ctx.reset_counters()
+        frame(); ctx.synchronize()
+        cnt = ctx.counters()
+        ctx.set_counting(False, False)
+        return cnt
+
+    def timed(self, frame, steps, warmup, clocks=False):
+        """device time of `steps` calls (max over ranks), host time spent enqueueing them, clocks during the window"""
+        ctx = self.ctx
+        ctx.sobol_reset(); self.worker.clear()
+        for _ in range(warmup):
+            frame()
+        ctx.reset_counters()
+        sampler = None
+        if clocks:
+            sampler = ClockSampler(self.local); sampler.start()
+        ev0, ev1 = self.event(), self.event()
+        self.barrier()
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            frame()
+        ctx.flush()
+        host_ms = (time.perf_counter() - t0) * 1e3
+        ev1.record()
+        self.barrier()
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1))
+        out = {'ms': ms, 'host_enqueue_ms_per_step': host_ms / steps, 'launches': ctx.launches()}
+        if sampler is not None:
+            out['clocks'] = sampler.finish()
+        return out
+
+    def stage_pass(self, frame, nprof):
+        ctx = self.ctx
+        ctx.set_counting(False, True); ctx.reset_counters()
+        for _ in range(nprof):
+            frame()
+        ctx.synchronize()
+        stage = ctx.stage_ms()
+        ctx.set_counting(False, False)
+        return {k: v / nprof for k, v in stage.items()}
+
+    def split_times(self, eng, total, reps=3):
+        """render and reduce timed separately (events around each), max over ranks: what a sharded step is made of"""
+        ctx, pdist = self.ctx, self.pdist
+        frame_nr = self.make_frame(eng, total, reduce=False)
+        a, b, c = self.event(), self.event(), self.event()
+        r_ms = d_ms = 0.0
+        for _ in range(reps):
+            self.barrier()
+            a.record(); frame_nr(); ctx.flush(); b.record()
+            if self.world > 1:
+                pdist.reduce_film_pass(0, 0)
+            c.record()
+            self.barrier()
+            r_ms += self.max_over_ranks(a.elapsed_time(b)); d_ms += self.max_over_ranks(b.elapsed_time(c))
+        return r_ms / reps, d_ms / reps
+
+    def film_check(self, eng, total):
+        """max relative difference between the reduced film of a sharded step and rank 0 rendering the same Sobol indices alone"""
+        ctx, torch = self.ctx, self.torch
+        ctx.sobol_reset(); self.worker.clear()
+        k0 = ctx.sobol_time + 1
+        red = self.make_frame(eng, total)()
+        self.barrier()
+        err = w_ok = None
+        if self.rank == 0:
+            red = red.clone()
+            self.worker.clear()
+            ctx.render_range(eng, k0, total, 1)
+            one = ctx.film_tensor(0)
+            scale = one[:, :3].abs().max().clamp_min(1e-6)
+            err = float(((red[:, :3] - one[:, :3]).abs().max() / scale).item())
+            w_ok = bool(torch.equal(red[:, 3], one[:, 3]) and float(one[:, 3].min().item()) == float(total))
+        self.barrier()
+        return {'max_rel_diff': err, 'sample_counts_equal': w_ok, 'samples': total, 'tolerance': 1e-5,
+                'ok': (err is not None and err <= 1e-5 and w_ok) if self.rank == 0 else None}
+
+    # ---- a path-traced config, end to end ----
+    def measure_pt(self, sc, mode, steps, warmup, stages=False, clocks=False, check=True):
+        eng = self.load(sc)
+        spp, world = sc['spp'], self.world
+        total = spp * world if mode == 'weak' else spp
+        frame = self.make_frame(eng, total)
+        cnt = self.count_rays(frame)
+        rays_step = self.sum_over_ranks(cnt['rays'])
+        t = self.timed(frame, steps, warmup, clocks=clocks)
+        ms_step = t['ms'] / steps
+        nx, ny = sc['size']
+        out = {'mode': mode, 'n_gpus': world, 'resolution': [nx, ny], 'tris': int(len(sc['mtlids'])), 'engine': sc['engine'], 'spp_per_step_total': total,
+               'Mrays_per_s': rays_step / (ms_step * 1e-3) / 1e6, 'spp_per_s': total / (ms_step * 1e-3), 'ms_per_step': ms_step, 'rays_per_step': rays_step,
+               'host_enqueue_ms_per_step': t['host_enqueue_ms_per_step'], 'steps': steps, 'warmup': warmup,
+               'per_ray_rank0': {'node_visits': cnt['node_visits'] / max(1, cnt['rays']), 'tri_tests': cnt['tri_tests'] / max(1, cnt['rays'])}}
+        out['_raw'] = {'cnt': cnt, 'timed': t, 'frame': frame, 'eng': eng, 'total': total}
+        if stages:
+            out['stage_ms_per_step'] = self.stage_pass(frame, max(1, min(steps, 5)))
+        if world > 1:
+            r_ms, d_ms = self.split_times(eng, total)
+            out['render_ms'], out['reduce_ms'] = r_ms, d_ms
+            out['reduce_bytes'] = nx * ny * 16
+            if check:
+                out['film_check'] = self.film_check(eng, total)
+        return out
+
+    def limits(self, out, single_ms):
+        """what keeps a sharded step from single_ms / N: smaller wavefronts (kernel tails, fewer rays per persistent kernel), the film
+        reduce, or the host not enqueueing fast enough -- each in ms per step"""
+        n = self.world
+        ideal = single_ms / n
+        tail = max(0.0, out.get('render_ms', out['ms_per_step']) - ideal)
+        host_gap = max(0.0, out['host_enqueue_ms_per_step'] - out.get('render_ms', out['ms_per_step']))
+        parts = {'ideal_ms (1-GPU time / N)': ideal, 'kernel_tail_ms (render - ideal)': tail, 'reduce_ms': out.get('reduce_ms', 0.0), 'host_enqueue_gap_ms': host_gap}
+        worst = max(('kernel_tail_ms (render - ideal)', 'reduce_ms', 'host_enqueue_gap_ms'), key=lambda k: parts[k])
+        return dict(parts, limiter=worst.split(' ')[0], single_gpu_ms=single_ms)
+
+    def single_gpu_ms(self, sc, total, reps=2):
+        """rank 0 alone renders the whole step (the others wait): the strong-scaling reference measured in the same run"""
+        eng = self.load(sc)
+        ms = 0.0
+        if self.rank == 0:
+            ctx = self.ctx
+            ctx.render_range(eng, 65, total, 1); ctx.synchronize()
+            a, b = self.event(), self.event()
+            a.record()
+            for _ in range(reps):
+                ctx.render_range(eng, 65, total, 1)
+            b.record(); self.torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+        self.barrier()
+        return self.max_over_ranks(ms)
+
+    # ---- config 5 ----
+    def measure_mlt(self, calls=16, warmup=3):
+        from ptina_b200.engine import MLTPathEngine
+        sc = self.scenes.metropolis()
+        self.load(dict(sc, engine='path'))
+        nch = 1 << 18
+        per = nch // self.world
+        eng = MLTPathEngine(nchains=nch, seed=0, chains=(self.rank * per, per))
+        eng.chains = (self.rank * per, per)
+        eng.reset()
+        ctx = self.ctx
+        self.worker.clear()
+        ctx.set_counting(True, False); ctx.reset_counters()
+        eng.render(1); ctx.synchronize()
+        rays_call = self.sum_over_ranks(ctx.counters()['rays'])
+        ctx.set_counting(False, False)
+        for _ in range(warmup):
+            eng.render(1)
+        a, b, c = self.event(), self.event(), self.event()
+        self.barrier()
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(calls):
+            eng.render(1)
+        host_ms = (time.perf_counter() - t0) * 1e3
+        b.record()
+        if self.world > 1:
+            self.pdist.reduce_film_pass(0, 0)
+        c.record()
+        self.barrier()
+        ms, red = self.max_over_ranks(a.elapsed_time(b)), self.max_over_ranks(b.elapsed_time(c))
+        return {'mode': 'strong (2^18 chains split over the GPUs)', 'n_gpus': self.world, 'chains_total': nch, 'chains_per_gpu': per, 'dims': 32, 'render_calls': calls,
+                'ms_per_render': ms / calls, 'Mproposals_per_s': nch * calls / (ms * 1e-3) / 1e6, 'Mrays_per_s': rays_call * calls / (ms * 1e-3) / 1e6,
+                'host_enqueue_ms_per_render': host_ms / calls, 'reduce_ms_per_readback': red, 'resolution': list(sc['size']),
+                'parity': 'chain trajectories unpinned (ti.random); per-chain radiance, accept/reject and splats are checked in tests/test_gpu_parity.py::test_mlt_engine'}
+
+
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
-    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from ptina_b200 import scenes, worker, _native
-    from ptina_b200 import dist as pdist
+    B = Bench(args)
+    torch, ctx, worker, native = B.torch, B.ctx, B.worker, B.native
+    rank, world = B.rank, B.world
     sc = workload(args)
     nx, ny = sc['size']
     spp = sc['spp']
-    eng = {'path': _native.ENGINE_PATH, 'brute': _native.ENGINE_BRUTE}[sc['engine']]
-    worker.init(device=local)
-    ctx = _native.context()
-    scenes.apply(worker, sc)
+
+    if args.one_step:           # ncu --profile-from-start off: exactly one warm step between cudaProfilerStart / Stop
+        eng = B.load(sc)
+        frame = B.make_frame(eng, spp * world)
+        for _ in range(max(1, args.warmup)):
+            frame()
+        ctx.synchronize()
+        torch.cuda.profiler.start()
+        frame(); ctx.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({'one_step': sc['name'], 'spp': spp}))
+        return
+
+    head = B.measure_pt(sc, 'weak', args.steps, args.warmup, stages=True, clocks=True, check=not args.quick)
+    raw = head.pop('_raw')
+    cnt, frame, eng = raw['cnt'], raw['frame'], raw['eng']
+    ms = raw['timed']['ms']
+    launches = raw['timed']['launches']
+    clocks = raw['timed']['clocks']
+    stage = head['stage_ms_per_step']
+    total_rays_per_step = head['rays_per_step']
+    value = head['Mrays_per_s']
     info = ctx.tree
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def frame():
-        # one step: this rank's share of the frame (rank-interleaved Sobol indices), then the film reduce
-        k0 = ctx.sobol_time + 1
-        first, count, stride = pdist.shard_range(k0, spp * world, rank, world)
-        ctx.render_range(eng, first, count, stride)
-        ctx.sobol_time = ctx.sobol_time + spp * world
-        if world > 1:
-            pdist.reduce_film_pass(0, 0)
-
-    # ---- counters (untimed pass with the counting instantiation; the workload is deterministic) ----
-    ctx.sobol_reset(); worker.clear()
-    ctx.set_counting(True, False); ctx.reset_counters()
-    frame(); ctx.synchronize()
-    cnt = ctx.counters()
-    ctx.set_counting(False, False)
-    rays_per_step = cnt['rays']
-
-    # ---- device-timed steps, inputs resident in HBM ----
-    ctx.sobol_reset(); worker.clear()
-    for _ in range(args.warmup):
-        frame()
-    ctx.set_counting(False, False); ctx.reset_counters()
-    sampler = ClockSampler(local); sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        frame()
-    ev1.record()
-    barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=10)      # an nvidia-smi query still in flight perturbs the host-synchronous e2e loop below
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launches()
-    # per-stage device times: a separate pass with CUDA events around every stage.  It runs the stages one after the other; the
-    # timed region above overlaps the shadow stage of a bounce with the extend stage of the next one (two streams), where a
-    # per-kernel duration is not defined.
-    nprof = max(1, min(args.steps, 5))
-    ctx.set_counting(False, True); ctx.reset_counters()
-    for _ in range(nprof):
-        frame()
-    ctx.synchronize()
-    stage = ctx.stage_ms()
-    ctx.set_counting(False, False)
-    t = torch.tensor([ms], device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    # every rank traces (statistically) the same number of rays per step; count this rank's exactly and sum over ranks
-    r = torch.tensor([float(rays_per_step)], device='cuda', dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    total_rays_per_step = float(r.item())
-    value = total_rays_per_step * args.steps / (ms * 1e-3) / 1e6
+    # ---- sustained window: the same step for >= 2 s ----
+    sustained = None
+    if not args.quick:
+        n_sus = max(args.steps, int(2200.0 / max(head['ms_per_step'], 1e-3)) + 1)
+        t = B.timed(frame, n_sus, 1, clocks=True)
+        sustained = {'value': total_rays_per_step * n_sus / (t['ms'] * 1e-3) / 1e6, 'unit': UNIT, 'seconds': t['ms'] * 1e-3, 'steps': n_sus,
+                     'ms_per_step': t['ms'] / n_sus, 'clocks': t['clocks']}
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + build + render + D2H inside the timed region ----
     verts_pin = torch.from_numpy(np.ascontiguousarray(sc['vertices'], dtype=np.float32)).pin_memory()
@@ -238,44 +449,122 @@ def run_gpu(args):
     img_pin = torch.empty((nx, ny, 4), dtype=torch.float32).pin_memory()
     from ptina_b200.model import ModelPool
     from ptina_b200.tree import BVHTree
+    from ptina_b200.engine import PathEngine, BruteEngine
+    engine_cls = BruteEngine if sc['engine'] == 'brute' else PathEngine
 
-    e2e_parts = {}
+    def e2e_run(percall):
+        parts = {}
 
-    def e2e_step():
-        t = [time.perf_counter()]
-        ModelPool().load(verts_pin.numpy(), mtl_pin.numpy()); t.append(time.perf_counter())
-        BVHTree().build(); t.append(time.perf_counter())
-        worker.clear()
-        frame(); t.append(time.perf_counter())
-        if rank == 0:
-            ctx.get_image(0, out=img_pin.numpy())
-        else:
-            ctx.synchronize()
-        t.append(time.perf_counter())
-        for name, a, b in zip(('load', 'build', 'launch', 'wait+readback'), t[:-1], t[1:]):
-            e2e_parts.setdefault(name, []).append(round((b - a) * 1e3, 2))
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    dbg = []
-    for _ in range(args.steps):
-        t1 = time.perf_counter()
-        e2e_step()
-        dbg.append((time.perf_counter() - t1) * 1e3)
-    e1.record()
-    if os.environ.get('PTB_BENCH_DEBUG'):
-        print('e2e per-step wall ms:', [round(x, 2) for x in dbg], {k: v[-args.steps:] for k, v in e2e_parts.items()}, file=sys.stderr)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    e2e_steps_ms = [round(x, 3) for x in dbg]
-    t = torch.tensor([e2e_ms], device='cuda')
+        def step():
+            t = [time.perf_counter()]
+            ModelPool().load(verts_pin.numpy(), mtl_pin.numpy()); t.append(time.perf_counter())
+            BVHTree().build(); t.append(time.perf_counter())
+            worker.clear()
+            tot = None
+            if percall:
+                for _ in range(spp):              # exams/benchmark.py:29-33: one sample per call
+                    engine_cls().render()
+            else:
+                tot = frame()
+            t.append(time.perf_counter())
+            if world > 1:                          # rank 0 resolves the reduced film (rgb / w) and reads it back; the others drain
+                if rank == 0:
+                    img_pin.copy_(B.pdist.resolve(tot))
+                else:
+                    ctx.synchronize()
+            else:
+                ctx.get_image(0, out=img_pin.numpy())
+            t.append(time.perf_counter())
+            for name, a, b in zip(('load', 'build', 'launch', 'wait+readback'), t[:-1], t[1:]):
+                parts.setdefault(name, []).append(round((b - a) * 1e3, 3))
+        return step, parts
+
+    def e2e_measure(percall):
+        step, parts = e2e_run(percall)
+        for _ in range(max(1, args.warmup)):
+            step()
+        B.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = B.event(), B.event()
+        e0.record()
+        per = []
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            step()
+            per.append((time.perf_counter() - t1) * 1e3)
+        e1.record()
+        B.barrier()
+        tot_ms = B.max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        return {'value': total_rays_per_step * args.steps / (tot_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': tot_ms / args.steps,
+                'ms_steps': [round(x, 3) for x in per], 'parts_ms_last_step': {k: v[-1] for k, v in parts.items()}}
+
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = total_rays_per_step * args.steps / (e2e_ms * 1e-3) / 1e6
+        # percall at N > 1 is not a reference pattern (the reference is single-device): batch only
+        e2e = e2e_measure(False)
+        e2e_percall = None
+    else:
+        e2e = e2e_measure(False)
+        e2e_percall = e2e_measure(True)
+    e2e.update({'h2d_bytes_per_step': int(verts_pin.numel() * 4 + mtl_pin.numel() * 4), 'd2h_bytes_per_step': int(img_pin.numel() * 4),
+                'path': 'ModelPool.load(pinned host) + BVHTree.build + FilmTable.clear + render_range(32 spp' + (', sharded) + NCCL film reduce + resolve' if world > 1 else ')') + ' + get_image(host)'})
+    if e2e_percall:
+        e2e_percall.update({'h2d_bytes_per_step': e2e['h2d_bytes_per_step'], 'd2h_bytes_per_step': e2e['d2h_bytes_per_step'], 'calls_per_step': spp,
+                            'ratio_to_batch_e2e': e2e_percall['value'] / e2e['value'],
+                            'path': f'ModelPool.load + BVHTree.build + FilmTable.clear + {spp} x {engine_cls.__name__}().render() + get_image(host)  (exams/benchmark.py:29-34)'})
+
+    # ---- the other configs at this N ----
+    configs = None
+    if not args.quick:
+        configs = {}
+        steps_small = max(3, min(args.steps, 5))
+        head_cfg = {k: v for k, v in head.items()}
+        head_cfg['e2e_Mrays_per_s'] = e2e['value']
+        configs['config2_cornell_monkey'] = head_cfg
+        for key, name in (('config1_cornell_boxes', 'cornell_boxes'), ('config3_matball', 'matball')):
+            if name == sc['name']:
+                continue
+            r = B.measure_pt(workload(args, name), 'weak', steps_small, 2, stages=True)
+            r.pop('_raw')
+            configs[key] = r
+        # config 2, strong: ONE 32-spp frame split over the N GPUs
+        if world > 1:
+            s2 = workload(args, 'cornell_monkey')
+            single = B.single_gpu_ms(s2, s2['spp'])
+            r = B.measure_pt(s2, 'strong', steps_small, 2)
+            r.pop('_raw')
+            r['limits'] = B.limits(r, single)
+            configs['config2_strong_one_frame_split'] = r
+        # config 4: a 32-spp step of the 1080p frame split over the N GPUs + the 33 MB reduce; then the whole 1024-spp render
+        s4 = workload(args, 'mega')
+        single4 = B.single_gpu_ms(s4, s4['spp'], reps=1) if world > 1 else None
+        r = B.measure_pt(s4, 'strong', 3, 1, stages=(world == 1))
+        raw4 = r.pop('_raw')
+        if world > 1:
+            r['limits'] = B.limits(r, single4)
+        c4, st4 = raw4['cnt'], r.get('stage_ms_per_step')
+        if st4:
+            # L2 roofline of the traversal stages, SURVEY 8(d): B_ray = 64 N_int + 48 N_tri + 48 bytes
+            trav_ms = st4['extend'] + st4['shadow']
+            alg = 64.0 * c4['node_visits'] + 48.0 * c4['tri_tests'] + 48.0 * c4['rays']
+            l2 = ctx.measure_l2(64, 20)
+            fmt = 32.0 * c4['node_visits'] + 64.0 * c4['tri_tests'] + 48.0 * c4['rays']
+            r['roofline_l2'] = {'bound': 'l2', 'achieved': alg / (trav_ms * 1e-3) / 1e9, 'peak': l2, 'unit': 'GB/s', 'frac': alg / (trav_ms * 1e-3) / 1e9 / l2,
+                                'formula': 'SURVEY 8(d): 64 B x node visits + 48 B x triangle tests + 48 B x rays, counters_per_step / (extend + shadow stage time, serial pass)',
+                                'bytes_in_this_format': fmt, 'format_note': 'nodes are fetched as 32-B quantised Node32 (one 256-bit load), triangles as 64-B Tri64',
+                                'counters_per_step': {k: c4[k] for k in ('rays', 'node_visits', 'tri_tests')}, 'traversal_ms_per_step': trav_ms,
+                                'peak_source': 'ptb_measure_l2: 148 x 8 blocks x 256 threads stream a 64 MiB buffer 20 times with 16-byte ld.global.cg loads after 2 warm passes (CUDA events)'}
+        # the full config: 1024 spp, Sobol points 65..1088, sharded, one reduce at the end
+        eng4 = B.load(s4)
+        full_frame = B.make_frame(eng4, 1024)
+        samp = ClockSampler(B.local); samp.start()
+        a, b = B.event(), B.event()
+        B.barrier(); a.record(); full_frame(); ctx.flush(); b.record(); B.barrier()
+        full_ms = B.max_over_ranks(a.elapsed_time(b))
+        r['full_1024spp'] = {'seconds': full_ms * 1e-3, 'spp_per_s': 1024 / (full_ms * 1e-3), 'Mrays_per_s': r['rays_per_step'] / r['spp_per_step_total'] * 1024 / (full_ms * 1e-3) / 1e6,
+                             'includes': 'render of 1024 spp split over the GPUs + one film reduce', 'clocks': samp.finish()}
+        configs['config4_mega'] = r
+        configs['config5_metropolis'] = B.measure_mlt()
+        B.load(sc)
 
     if rank == 0:
         peaks = {}
@@ -284,45 +573,57 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak, peak_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json)') if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md)')
-        l2_gbs = ctx.measure_l2(64, 20)
-        # dominant stage = BVH traversal (extend + shadow; each stage launch = k_trace_pre + k_trace_tree): algorithmic bytes per
-        # launch = 64 B per node visit + 64 B per triangle test + 48 B per ray (32 B ray in, 16 B hit out)  -- DESIGN.md "Roofline"
-        n_trav_launches = 5 * nprof * (2 if eng == _native.ENGINE_PATH else 1)
-        ncu = {}
-        try:    # DRAM bytes / issue-slot utilisation of the traversal kernels from the committed ncu capture of this build
-            ncu = json.load(open(os.path.join(ROOT, 'profiles', 'traversal_ncu.json'))).get(sc['name'], {})
+        # What binds config 2 is instruction issue (the scene is 125 KB: nodes in shared memory, triangles in L1).  Roof = 4 warp
+        # instructions per clock per SM x SMs x the SM clock sampled during the timed region.  Warp instructions per step are a property
+        # of the (deterministic) workload: counted once with ncu (smsp__inst_executed.sum over every launch of one step, tools/
+        # ncu_inst_counts.py -> profiles/inst_counts.json) and divided here by the LIVE step time.
+        inst = {}
+        try:
+            inst = json.load(open(os.path.join(ROOT, 'profiles', 'inst_counts.json'))).get(sc['name'], {})
         except Exception:
             pass
+        sm_mhz = clocks.get('sm_mhz') or 1965
+        issue_peak = 4.0 * 148 * sm_mhz * 1e6 / 1e9            # G warp-instructions / s
+        roofline = {'bound': 'issue', 'unit': 'Gwarp-inst/s', 'peak': issue_peak, 'peak_source': f'4 warp-instr/clk/SM x 148 SMs x {sm_mhz} MHz (SM clock sampled during the timed region)',
+                    'kernel': 'whole step (k_trace_pre + k_trace_tree + k_shade are 97 % of it)', 'timing': 'CUDA events over the timed region (ms_per_step)'}
+        if inst.get('warp_inst_per_step') and inst.get('spp') == spp:
+            ach = inst['warp_inst_per_step'] / (head['ms_per_step'] * 1e-3) / 1e9
+            lanes = inst['thread_inst_per_step'] / inst['warp_inst_per_step']
+            roofline.update({'achieved': ach, 'frac': ach / issue_peak, 'warp_inst_per_step': inst['warp_inst_per_step'], 'lanes_per_inst': lanes,
+                             'frac_lane_weighted': ach / issue_peak * lanes / 32.0, 'inst_source': inst.get('source'),
+                             'traffic': inst.get('dram_bytes_per_step'), 'per_kernel': inst.get('per_kernel')})
+        else:
+            roofline.update({'achieved': None, 'frac': None, 'traffic': None, 'note': 'profiles/inst_counts.json has no entry for this scene / spp'})
+        # the schema's HBM view of the traversal stages, with SURVEY 8(d)'s formula (served from shared memory / L1, so not the binding roof)
         trav_ms = stage['extend'] + stage['shadow']
-        alg_bytes_step = 64.0 * cnt['node_visits'] + 64.0 * cnt['tri_tests'] + 48.0 * cnt['rays']
-        achieved = alg_bytes_step * nprof / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        alg = 64.0 * cnt['node_visits'] + 48.0 * cnt['tri_tests'] + 48.0 * cnt['rays']
+        roofline['traversal_bytes_view'] = {'algorithmic_GBps': alg / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None, 'hbm_peak_GBps': hbm_peak, 'peak_source': peak_src,
+                                            'formula': '64 B x node visits + 48 B x triangle tests + 48 B x rays (SURVEY 8d) / (extend + shadow stage time)',
+                                            'note': 'not a roofline for this config: the 125 KB scene is served from shared memory and L1; DRAM traffic is `traffic`'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': config_of(sc, world),
                 'spp_per_s': spp * world * args.steps / (ms * 1e-3),
                 'rays_per_step': total_rays_per_step,
-                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(verts_pin.numel() * 4 + mtl_pin.numel() * 4),
-                        'd2h_bytes_per_step': int(img_pin.numel() * 4), 'ms_per_step': e2e_ms / args.steps, 'ms_steps': e2e_steps_ms,
-                        'path': 'ModelPool.load(pinned host) + BVHTree.build + FilmTable.clear + PathEngine.render_range + FilmTable.get_image(host)'},
+                'e2e': e2e, 'e2e_percall': e2e_percall, 'sustained': sustained,
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': (achieved / hbm_peak) if achieved else None, 'traffic': ncu.get('dram_bytes_per_launch'),
-                             'kernel': 'k_trace_pre + k_trace_tree (BVH traversal: extend and shadow stages)', 'ncu': ncu or None, 'launches': n_trav_launches, 'avg_launch_ms': trav_ms / n_trav_launches,
-                             'algorithmic_bytes_per_launch': alg_bytes_step * nprof / n_trav_launches,
-                             'timing': f'CUDA events around every stage, serial pass of {nprof} steps after the timed region', 'peak_source': peak_src,
-                             'l2_peak_gbs_measured': l2_gbs, 'frac_of_l2': (achieved / l2_gbs) if achieved else None,
-                             'note': 'gather workload served from shared memory / L1 / L2 (the scene is cache resident): HBM is the schema bound; '
-                                     'what binds is instruction issue (ncu: issue-slot utilisation, lanes per instruction -- profiles/)'},
-                'stage_ms_per_step': {k: v / nprof for k, v in stage.items()},
+                'roofline': roofline,
+                'stage_ms_per_step': stage,
                 'schedule': 'shadow stage of bounce b overlapped with the extend stage of bounce b+1 (2 streams); stage_ms_per_step from a serial pass',
                 'counters_per_step_rank0': cnt,
-                'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms},
-                'clocks': sampler.summary()}
+                'tree': {'n': info.n, 'depth': info.depth, 'valid': info.valid, 'policy': info.policy, 'build_ms': info.build_ms, 'trav_depth': info.trav_depth, 'trav_ploc': info.trav_ploc},
+                'clocks': clocks}
+        for k in ('film_check', 'render_ms', 'reduce_ms', 'host_enqueue_ms_per_step'):
+            if k in head:
+                line[k] = head[k]
+        if configs is not None:
+            line['configs'] = configs
         if not args.no_cpu and world == 1:      # rank 0 at N=1 only (torchrun also pins OMP_NUM_THREADS=1)
             line['cpu_baseline'] = {k: v for k, v in cpu_reference(sc, args.cpu_seconds, max_frames=8).items() if k in ('value', 'unit', 'cores', 'kind', 'sample', 'spp_per_s', 'note')}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
 
 
 if __name__ == '__main__':

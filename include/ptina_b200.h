@@ -17,6 +17,10 @@
  *   - all device work is enqueued on the context's stream (ptb_set_stream; default = the legacy
  *     default stream).  Only readbacks (memspace == PTB_HOST outputs), ptb_build_tree and
  *     ptb_synchronize block the host.
+ *   - ptb_render only RECORDS its samples; consecutive calls (the reference's one-sample-per-call loop,
+ *     exams/benchmark.py:29-33) are submitted as one wavefront batch when the batch is full or when any
+ *     other entry point that could observe the difference is called (every entry point below flushes
+ *     first; ptb_flush does only that).  The film is bit-identical to call-by-call submission.
  *   - there is NO CPU fallback: without a CUDA device ptb_create fails.
  */
 #ifndef PTINA_B200_H
@@ -57,8 +61,9 @@ typedef struct ptb_tree_info {
     int32_t depth;        /* height of the tree in nodes, root = 1 (0 if !valid) */
     int32_t policy;       /* traversal policy in effect (PTB_TRAVERSE_REFERENCE / _ORDERED) */
     float build_ms;       /* device time of the whole build */
-    int32_t list_n;       /* triangles on the always-test list of the production traversal (big or ill-conditioned) */
-    int32_t list_overflow;/* 1 = more ill-conditioned triangles than the list holds: the production traversal is not used */
+    int32_t list_n;       /* triangles on the always-test list of the production traversal (big ones; at most 32, the rest stay in the tree) */
+    int32_t trav_depth;   /* height of the tree the production traversal walks (PLOC topology when trav_ploc, else the LBVH's = depth) */
+    int32_t trav_ploc;    /* 1 = the traversal tree was rebuilt by PLOC (same answers by the gate lemma, fewer node visits) */
 } ptb_tree_info;
 
 typedef struct ptb_counters {
@@ -80,6 +85,7 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out);
 int ptb_destroy(ptb_ctx* ctx);
 int ptb_set_stream(ptb_ctx* ctx, void* cuda_stream);
 int ptb_synchronize(ptb_ctx* ctx);                                  /* worker.py:17-18 */
+int ptb_flush(ptb_ctx* ctx);                                        /* submit recorded ptb_render calls without waiting */
 
 /* sampling/sobol.py:75-97: V = calc_sobol_vgrid(2^20, 21201) as the i32 field [rows=21][dim]; resets
  * the generator (time = 0 then `skip` = 64 updates). */
@@ -127,6 +133,12 @@ int ptb_film_ptr(ptb_ctx* ctx, int pass, void** dev_ptr, int64_t* ntexels);
 /* engine/path.py:75-77, brute.py:25-27, preview.py:19-21, mltpath.py:85-87: `nsamples` consecutive
  * Engine.render() calls (one Sobol update + one sample per pixel each). */
 int ptb_render(ptb_ctx* ctx, int engine, int nsamples);
+/* engine/path.py:96-118 render_tile(i, j, samples): one Sobol update, then samples m = 0..min(samples, 63) (inclusive, as the
+ * reference text has it) of every pixel of the 64x64 tile (i, j), sample m rotated by wanghash3(x, y, m); pixels outside the film
+ * are skipped.  engine/path.py:120-128 render_final(nsamples): every tile, render_tile(i, j, s) for s = nsamples, nsamples-64, ... > 0.
+ * (Both are commented out in the reference's engine/path.py and driven by exams/benchtiles.py:25-31.)  PATH or BRUTE engine. */
+int ptb_render_tile(ptb_ctx* ctx, int engine, int i, int j, int samples);
+int ptb_render_final(ptb_ctx* ctx, int engine, int nsamples);
 /* the same for explicit Sobol point indices k_first, k_first+stride, ... (count of them); does not touch
  * the generator's time.  Used to shard a sample range over GPUs. */
 int ptb_render_range(ptb_ctx* ctx, int engine, int k_first, int count, int stride);
@@ -134,13 +146,17 @@ int ptb_render_range(ptb_ctx* ctx, int engine, int k_first, int count, int strid
 int ptb_mlt_reset(ptb_ctx* ctx, uint64_t seed, int chain_first, int chain_count);
 int ptb_mlt_set_param(ptb_ctx* ctx, float lsp, float sigma);
 /* tap: the chains' last proposal X_new [count][32] and its radiance L_new [count][3] (mltpath.py:56-75), and the current
- * state X_old / L_old; any pointer may be NULL */
-int ptb_mlt_state(ptb_ctx* ctx, float* x_new, float* l_new, float* x_old, float* l_old);
+ * state X_old / L_old; any pointer may be NULL.  `count` = the chain count the buffers are sized for (must match ptb_mlt_reset's) */
+int ptb_mlt_state(ptb_ctx* ctx, int count, float* x_new, float* l_new, float* x_old, float* l_old);
 
 /* filmtable.py:47-63 get_image: out [nx][ny][4];  filmtable.py:65-79 fast_export_image: out [ny*nx*3] */
 int ptb_get_image(ptb_ctx* ctx, int pass, float* out, int memspace);
 int ptb_fast_export_image(ptb_ctx* ctx, int pass, float* out, int memspace);
 int ptb_get_film(ptb_ctx* ctx, int pass, float* out, int memspace);  /* raw sums [nx*ny][4] */
+/* blender.py:809-820 (TinaDrawData: fast_export_image into a NumPy array that is then uploaded as a GL buffer): the same resolve
+ * written straight into an OpenGL buffer object of the caller's current GL context (>= nx*ny*3 floats) through CUDA-GL interop --
+ * no host round trip.  Fails with a message when the calling thread has no GL context. */
+int ptb_fast_export_gl(ptb_ctx* ctx, int pass, unsigned int gl_buffer);
 
 /* ---- parity taps (tests) ----------------------------------------------------------------------- */
 /* primary rays of Sobol point k for every pixel (path.py:85-93 + camera.py:34-39) and their closest hits
@@ -161,6 +177,7 @@ int ptb_material_get(ptb_ctx* ctx, const int32_t* mtlid, const float* uv, int m,
 int ptb_light_hit(ptb_ctx* ctx, const float* rays, int m, float* out6);                            /* light/__init__.py:51-81 */
 int ptb_light_sample(ptb_ctx* ctx, const float* hitpos_samp, int m, float* out8);                  /* light/__init__.py:83-121 */
 int ptb_world_at(ptb_ctx* ctx, const float* dirs, int m, float* out3);                             /* light/world.py:22-29 */
+int ptb_normaldist(ptb_ctx* ctx, const float* samp, int m, float* out);                            /* common.py:337-352 erfinv + normaldist (MLT small steps) */
 /* per-pixel radiance of one sample without touching the film: out [nx*ny][3] */
 int ptb_render_sample(ptb_ctx* ctx, int engine, int k, float* out);
 

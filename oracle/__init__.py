@@ -241,6 +241,27 @@ class Oracle:
         assert r == 0
         return dict(zip(('rays', 'node_visits', 'box_tests', 'tri_tests', 'max_stack'), cnt.tolist()))
 
+    def render_preview(self, nsamples=1, k_first=None):
+        """`nsamples` calls of PreviewEngine.render() (preview.py:19-41): albedo -> film 1, normal -> film 2."""
+        if k_first is None:
+            k_first = self.sobol_time + 1
+            self.sobol_time += nsamples
+        assert self.L.ora_render_preview(self.h, int(k_first), int(nsamples)) == 0
+
+    def render_tile(self, engine, i, j, samples):
+        """PathEngine.render_tile (path.py:96-118): one Sobol update, then samples 0..min(samples, 63) of the 64x64 tile (i, j)."""
+        self.sobol_time += 1
+        assert self.L.ora_render_tile(self.h, engine, int(self.sobol_time), int(i), int(j), int(samples)) == 0
+
+    def render_final(self, engine, nsamples):
+        """path.py:120-128."""
+        for i in range((self.nx + 63) // 64):
+            for j in range((self.ny + 63) // 64):
+                samples = nsamples
+                while samples > 0:
+                    self.render_tile(engine, i, j, samples)
+                    samples -= 64
+
     def trace_from_samples(self, X):
         X = _f32(X)
         out = np.zeros((X.shape[0], 3), np.float32)
@@ -297,6 +318,20 @@ def sample_bsdf(params, geom):
     params, geom = _f32(params).reshape(-1, 14), _f32(geom).reshape(-1, 10)
     out = np.zeros((params.shape[0], 7), np.float32)
     lib().ora_sample_bsdf(_p(params), _p(geom), params.shape[0], _p(out))
+    return out
+
+
+def normaldist(samp):
+    samp = _f32(samp).reshape(-1)
+    out = np.zeros_like(samp)
+    lib().ora_normaldist(_p(samp), samp.shape[0], _p(out))
+    return out
+
+
+def erfinv(x):
+    x = _f32(x).reshape(-1)
+    out = np.zeros_like(x)
+    lib().ora_erfinv(_p(x), x.shape[0], _p(out))
     return out
 
 

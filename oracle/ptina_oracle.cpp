@@ -1123,6 +1123,79 @@ int ora_render(void* h, int engine, int k_first, int nsamples, int nthreads, lon
     return 0;
 }
 
+// engine/preview.py:19-41 PreviewEngine.render() x nsamples: Sobol points k_first .., primary hit of the camera ray AS GENERATED
+// (preview.py:33 does not re-normalise it, unlike path.py:28), film 1 += (albedo, 1), film 2 += (normal, 1); misses add (0, 1)
+int ora_render_preview(void* h, int k_first, int nsamples) {
+    Oracle* o = (Oracle*)h;
+    if ((int)o->sobolV.size() == 0 || o->nx * o->ny == 0) return -1;
+    std::vector<float> P(o->sobol_dim);
+    for (int s = 0; s < nsamples; s++) {
+        o->sobol_point(k_first + s, P.data());
+#pragma omp parallel for schedule(dynamic, 8)
+        for (int i = 0; i < o->nx; i++)
+            for (int j = 0; j < o->ny; j++) {
+                Oracle::Rng rng{P.data(), wanghash2(i, j), o->sobol_dim, nullptr, 0};
+                Ray r = o->primary_ray(i, j, rng);
+                V3 albedo = v3(0.0f), normal = v3(0.0f);
+                Hit hit = o->bvh_intersect(r, -1, nullptr);
+                if (hit.hit == 1) {
+                    V3 hitpos; float sign; Disney material;
+                    o->get_geometries(hit, r, &hitpos, &normal, &sign, &material);
+                    albedo = material.basecolor;
+                }
+                size_t q = (size_t)i * o->ny + j;
+                o->film[1][q] = o->film[1][q] + V4{albedo.x, albedo.y, albedo.z, 1.0f};
+                o->film[2][q] = o->film[2][q] + V4{normal.x, normal.y, normal.z, 1.0f};
+            }
+    }
+    return 0;
+}
+
+// engine/path.py:96-118 render_tile(i, j, samples) at Sobol point k (the reference text is commented out; exams/benchtiles.py:25
+// calls it): samples m = 0..min(samples, 63) inclusive (`if m > samples: continue`) of every pixel of the 64x64 tile, sample m drawn
+// through get_proxy(wanghash3(x, y, m)).  Pixels outside the film are skipped: the text's `x > nx` / `y > ny` lets x == nx write
+// past the image and y == ny alias pixel (x+1, 0); tests/golden/make_golden_r2.py records what the text itself does there.
+int ora_render_tile(void* h, int engine, int k, int ti, int tj, int samples) {
+    Oracle* o = (Oracle*)h;
+    if ((int)o->sobolV.size() == 0 || o->nx * o->ny == 0) return -1;
+    std::vector<float> P(o->sobol_dim);
+    o->sobol_point(k, P.data());
+    const int ms = std::min(samples, 63);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int kx = 0; kx < 64; kx++)
+        for (int l = 0; l < 64; l++) {
+            const int x = ti * 64 + kx, y = tj * 64 + l;
+            if (x >= o->nx || y >= o->ny) continue;
+            for (int m = 0; m <= ms; m++) {
+                Oracle::Rng rng{P.data(), wanghash(m ^ wanghash2(x, y)), o->sobol_dim, nullptr, 0};
+                Ray r = o->primary_ray(x, y, rng);
+                V3 clr = engine == 0 ? o->path_trace(r, rng, nullptr) : o->brute_trace(r, rng, nullptr);
+                V4& f = o->film[0][(size_t)x * o->ny + y];
+                f = f + V4{clr.x, clr.y, clr.z, 1.0f};
+            }
+        }
+    return 0;
+}
+
+// common.py:337-352, literal: erfinv (Winitzki, a = 0.147; the constants 2/(pi*0.147) and 1/0.147 are Python floats folded to f32
+// when they meet an f32 operand) and normaldist(samp) = sqrt(2) * erfinv(samp * 2 - 1)
+static inline float erfinv_ref(float x) {
+    float sgn = x < 0 ? -1.0f : 1.0f;
+    x = (1.0f - x) * (1.0f + x);
+    float lnx = logf(x);
+    float tt1 = (float)(2.0 / (3.14159265358979323846 * 0.147)) + 0.5f * lnx;
+    float tt2 = (float)(1.0 / 0.147) * lnx;
+    return sgn * sqrtf(-tt1 + sqrtf(tt1 * tt1 - tt2));
+}
+int ora_normaldist(const float* in, int m, float* out) {
+    for (int q = 0; q < m; q++) out[q] = sqrtf(2.0f) * erfinv_ref(in[q] * 2.0f - 1.0f);
+    return 0;
+}
+int ora_erfinv(const float* in, int m, float* out) {
+    for (int q = 0; q < m; q++) out[q] = erfinv_ref(in[q]);
+    return 0;
+}
+
 // per-pixel radiance of ONE sample (no film), for golden comparisons: out[nx*ny][3]
 int ora_render_sample(void* h, int engine, int k, float* out) {
     Oracle* o = (Oracle*)h;

@@ -29,7 +29,7 @@ class Caps(ctypes.Structure):
 
 class TreeInfo(ctypes.Structure):
     _fields_ = [('n', ctypes.c_int32), ('aabb_sweeps', ctypes.c_int32), ('valid', ctypes.c_int32), ('depth', ctypes.c_int32),
-                ('policy', ctypes.c_int32), ('build_ms', ctypes.c_float), ('list_n', ctypes.c_int32), ('list_overflow', ctypes.c_int32)]
+                ('policy', ctypes.c_int32), ('build_ms', ctypes.c_float), ('list_n', ctypes.c_int32), ('trav_depth', ctypes.c_int32), ('trav_ploc', ctypes.c_int32)]
 
 
 class Counters(ctypes.Structure):
@@ -42,13 +42,13 @@ class Counters(ctypes.Structure):
 
 # every symbol include/ptina_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_synchronize',
+    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_synchronize', 'ptb_flush',
     'ptb_set_sobol_table', 'ptb_sobol_reset', 'ptb_sobol_get_time', 'ptb_sobol_set_time', 'ptb_sobol_point',
     'ptb_load_model', 'ptb_load_materials', 'ptb_load_images', 'ptb_clear_lights', 'ptb_add_light', 'ptb_set_world_light',
     'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_export_traversal', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
-    'ptb_film_ptr', 'ptb_render', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_mlt_state', 'ptb_get_image',
-    'ptb_fast_export_image', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
-    'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_render_sample',
+    'ptb_film_ptr', 'ptb_render', 'ptb_render_tile', 'ptb_render_final', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_mlt_state', 'ptb_get_image',
+    'ptb_fast_export_image', 'ptb_fast_export_gl', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
+    'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_normaldist', 'ptb_render_sample',
     'ptb_set_counting', 'ptb_get_counters', 'ptb_reset_counters', 'ptb_get_stage_ms', 'ptb_get_launches', 'ptb_measure_l2', 'ptb_selftest',
 ]
 
@@ -155,6 +155,10 @@ class Context:
     def synchronize(self):
         self._check(self.L.ptb_synchronize(self.h))
 
+    def flush(self):
+        """Submit the render() calls recorded so far (they are merged into wavefront batches) without waiting for the device."""
+        self._check(self.L.ptb_flush(self.h))
+
     # ---- sobol -----------------------------------------------------------------------------------
     def set_sobol_table(self, V):
         V = i32(V)
@@ -185,6 +189,14 @@ class Context:
         dev = _is_cuda_tensor(verts)
         assert dev == _is_cuda_tensor(mtlids), 'vertices and mtlids must live in the same memory space'
         nfaces = int(mtlids.shape[0])
+        if dev:      # the library reads raw memory: a float64 or strided tensor would be silently misread
+            import torch
+            assert verts.dtype == torch.float32 and mtlids.dtype == torch.int32, 'device model data must be float32 / int32'
+            assert verts.is_contiguous() and mtlids.is_contiguous(), 'device model data must be contiguous'
+            assert verts.device.index == self.device and mtlids.device.index == self.device, 'model tensors live on another GPU'
+        else:
+            assert verts.dtype == np.float32 and mtlids.dtype == np.int32 and verts.flags.c_contiguous and mtlids.flags.c_contiguous
+        assert tuple(verts.shape) == (nfaces * 3, 8), 'vertices must be [nfaces*3, 8]'
         self._check(self.L.ptb_load_model(self.h, _ptr(verts), _ptr(mtlids), nfaces, DEVICE if dev else HOST))
         self._keep = (verts, mtlids)     # keep the sources alive until the async copy is consumed
         self.nfaces = nfaces
@@ -284,9 +296,19 @@ class Context:
         assert out.size >= nx * ny * 3 if isinstance(out, np.ndarray) else out.numel() >= nx * ny * 3
         self._check(self.L.ptb_fast_export_image(self.h, int(id), _ptr(out), DEVICE if _is_cuda_tensor(out) else HOST))
 
+    def fast_export_gl(self, gl_buffer, id=0):
+        """The same resolve written straight into an OpenGL buffer object of the current GL context (CUDA-GL interop)."""
+        self._check(self.L.ptb_fast_export_gl(self.h, int(id), ctypes.c_uint(int(gl_buffer))))
+
     # ---- render ----------------------------------------------------------------------------------
     def render(self, engine, nsamples=1):
         self._check(self.L.ptb_render(self.h, int(engine), int(nsamples)))
+
+    def render_tile(self, engine, i, j, samples):
+        self._check(self.L.ptb_render_tile(self.h, int(engine), int(i), int(j), int(samples)))
+
+    def render_final(self, engine, nsamples):
+        self._check(self.L.ptb_render_final(self.h, int(engine), int(nsamples)))
 
     def render_range(self, engine, k_first, count, stride=1):
         self._check(self.L.ptb_render_range(self.h, int(engine), int(k_first), int(count), int(stride)))
@@ -301,9 +323,10 @@ class Context:
         self._check(self.L.ptb_mlt_reset(self.h, ctypes.c_uint64(seed), int(chain_first), int(chain_count)))
 
     def mlt_state(self, nchains):
+        """nchains must be the chain count of the last mlt_reset (checked by the library)."""
         xn, xo = np.empty((nchains, 32), np.float32), np.empty((nchains, 32), np.float32)
         ln, lo = np.empty((nchains, 3), np.float32), np.empty((nchains, 3), np.float32)
-        self._check(self.L.ptb_mlt_state(self.h, _ptr(xn), _ptr(ln), _ptr(xo), _ptr(lo)))
+        self._check(self.L.ptb_mlt_state(self.h, int(nchains), _ptr(xn), _ptr(ln), _ptr(xo), _ptr(lo)))
         return dict(X_new=xn, L_new=ln, X_old=xo, L_old=lo)
 
     def mlt_set_param(self, lsp, sigma):
@@ -365,6 +388,9 @@ class Context:
 
     def world_at(self, dirs):
         return self._tap(self.L.ptb_world_at, dirs, 3, None, 0, 3)
+
+    def normaldist(self, samp):
+        return self._tap(self.L.ptb_normaldist, samp, 1, None, 0, 1).reshape(-1)
 
     # ---- counters ------------------------------------------------------------------------------------
     def set_counting(self, count=False, profile=False):

@@ -7,14 +7,22 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libptina_b200.so')
-SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu']
-HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', 'ptb_trace_kernel.cuh', '../../include/ptina_b200.h']
+SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu', 'shade.cu']
+HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', 'ptb_trace_kernel.cuh', 'ptb_wavefront.cuh', '../../include/ptina_b200.h']
 
 # -fmad=false / -prec-div / -prec-sqrt / -ftz=false: IEEE binary32 in source order -- what makes Morton codes, primary
 # rays and the box/triangle predicates bit-identical to a strict CPU evaluation (DESIGN.md "Arithmetic contract").
-NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-              '-fmad=false', '-prec-div=true', '-prec-sqrt=true', '-ftz=false',
-              '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
+NVCC_BASE = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-ftz=false',
+             '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
+STRICT = ['-fmad=false', '-prec-div=true', '-prec-sqrt=true']
+# shade.cu only, and only on request (`--fast-shade` / PTB_FAST_SHADE=1): FMA contraction, approximate division and square root in the
+# arithmetic that owes the reference 1e-5, not bits (see the header of csrc/shade.cu).  Not the default: DESIGN.md section 6 has the numbers.
+FAST = ['-fmad=true', '-prec-div=false', '-prec-sqrt=false', '-DPTB_SHADE_FAST=1']
+NVCC_FLAGS = NVCC_BASE + STRICT
+
+
+def flags_for(src, fast_shade):
+    return NVCC_BASE + (FAST if (fast_shade and src == 'shade.cu') else STRICT)
 
 
 def _nvcc():
@@ -32,9 +40,11 @@ def stale():
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False, defines=(), out=None):
+def build(force=False, verbose=False, defines=(), out=None, fast_shade=None):
     """defines / out: tuning variants (`-DNAME=value` ... into another .so, selected at run time with PTINA_B200_LIB)."""
-    if not force and not stale() and not defines and out is None:
+    if fast_shade is None:
+        fast_shade = os.environ.get('PTB_FAST_SHADE', '0') == '1'
+    if not force and not stale() and not defines and out is None and not fast_shade:
         return SO
     out = out or SO
     tag = '' if out == SO else '_' + os.path.basename(out).replace('.so', '')
@@ -49,7 +59,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(HERE, 'build', src.replace('.cu', tag + '.o'))
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + ccbin + flags_for(src, fast_shade) + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:
@@ -66,4 +76,5 @@ def build(force=False, verbose=False, defines=(), out=None):
 if __name__ == '__main__':
     defs = [a[2:] for a in sys.argv if a.startswith('-D')]
     outs = [a[6:] for a in sys.argv if a.startswith('--out=')]
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None,
+                fast_shade=True if '--fast-shade' in sys.argv else None))

@@ -1,0 +1,2 @@
+from ptina.common import *  # noqa: F401,F403
+from ptina_b200.image import *  # noqa: F401,F403

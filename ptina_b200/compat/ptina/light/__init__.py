@@ -1,0 +1,2 @@
+from ptina.common import *  # noqa: F401,F403
+from ptina_b200.light import *  # noqa: F401,F403

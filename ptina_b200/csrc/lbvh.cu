@@ -31,7 +31,7 @@ __device__ __forceinline__ V3 face_center(const float* __restrict__ verts, int f
 }
 
 // scalars layout (floats): [0..2] centre min, [3..5] centre max ; ints: [8] remaining, [9] invalid flag, [10] root height,
-// [11] always-test list length, [12] list overflow, [13] sweeps, [14] node planes outside the quantisation grid, [15] height of the PLOC traversal tree
+// [11] always-test list length, [12] unused, [13] sweeps, [14] node planes outside the quantisation grid, [15] height of the PLOC traversal tree
 __global__ void k_init_scalars(float* s) {
     s[0] = s[1] = s[2] = PTB_INF;
     s[3] = s[4] = s[5] = -PTB_INF;
@@ -233,16 +233,13 @@ __global__ void __launch_bounds__(BLK) k_validate(const int* __restrict__ parent
 // point outside the triangle (derivation in DESIGN.md section 10):
 //   eps_T = 256u * cond * (|u| + |v|) + 64u * (|v0|_inf + |u| + |v|),  cond = uu*vv / |D| = 1 / sin^2(angle(u, v)),  u = 2^-24
 // valid while cond * (36 + 20 * max(|u|/|v|, |v|/|u|)) <= 1e6.  Flags (w of tlo): 1 = NEVER (D == 0 or not finite: s, t are
-// inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> the leaf is bounded by its GATE box instead, the
-// reference box of its parent, which any accepted triangle's ray must pass anyway), 4 = BIG (bounds cover more than 1/16 of the
-// scene's box area: hurts every ancestor's box -> always-test list if there is room).
+// inf / NaN, no ray is ever accepted), 2 = MUST (ill-conditioned: no usable bound -> the leaf STAYS IN THE TREE, bounded by its GATE
+// box instead -- the reference box of its parent, which any accepted triangle's ray must pass anyway -- and exempt from distance
+// culling), 4 = BIG (box surface above PTB_BIG_FRACTION = 1/4 of the scene's: hurts every ancestor's box -> always-test list while
+// there is room; BIG triangles beyond PTB_LIST_CAP simply stay in the tree, which is still conservative, so the list cannot overflow).
 #ifndef PTB_BIG_FRACTION
 #define PTB_BIG_FRACTION (1.0f / 4.0f)      /* a triangle is BIG when its box surface exceeds this fraction of the scene's (walls: 1/3) */
 #endif
-#define PTB_TF_NEVER 1
-#define PTB_TF_MUST 2
-#define PTB_TF_BIG 4
-#define PTB_TF_LISTED 8
 __global__ void __launch_bounds__(BLK) k_tri_prep(const float* __restrict__ verts, const int* __restrict__ leaf, int n, const float* __restrict__ scal,
                                                   float4* __restrict__ tlo, float4* __restrict__ thi) {
     int s = blockIdx.x * BLK + threadIdx.x;
@@ -567,8 +564,12 @@ int ptb_lbvh_build(ptb_ctx* c) {
     c->tree_n = n;
     c->tree_info = ptb_tree_info{};
     c->tree_info.n = n;
-    cudaEvent_t e0, e1;
-    PTB_CUDA(cudaEventCreate(&e0)); PTB_CUDA(cudaEventCreate(&e1));
+    struct Events {          // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    PTB_CUDA(cudaEventCreate(&ev.a)); PTB_CUDA(cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     PTB_CUDA(cudaEventRecord(e0, st));
     float* scal = (float*)c->d_scalars;
     int nint = n > 1 ? n - 1 : 1;
@@ -618,7 +619,6 @@ int ptb_lbvh_build(ptb_ctx* c) {
             }
         }
         if (remaining != 0) {
-            cudaEventDestroy(e0); cudaEventDestroy(e1);
             c->tree_info.aabb_sweeps = sweeps;
             ptb_set_error("AABB step never stop! hierarchy corrupted?");
             return 2;
@@ -662,7 +662,6 @@ int ptb_lbvh_build(ptb_ctx* c) {
         if (n > 1 && n - 1 <= PTB_SMALL_TREE) {
             sweeps = h_scal[13];
             if (h_scal[8] != 0) {
-                cudaEventDestroy(e0); cudaEventDestroy(e1);
                 c->tree_info.aabb_sweeps = sweeps;
                 ptb_set_error("AABB step never stop! hierarchy corrupted?");
                 return 2;
@@ -671,7 +670,6 @@ int ptb_lbvh_build(ptb_ctx* c) {
         valid = (n > 1) && h_scal[9] == 0;
         depth = valid ? h_scal[10] : 0;
         c->list_n = n > 1 ? h_scal[11] : 0;
-        c->list_overflow = n > 1 ? h_scal[12] : 0;
         for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
         // the PLOC tree replaces the LBVH topology for traversal when it was built and fits the traversal stack
         c->trav_depth = (n > 1 && n - 1 <= PTB_SMALL_TREE && c->use_ploc) ? h_scal[15] : -1;
@@ -710,13 +708,13 @@ int ptb_lbvh_build(ptb_ctx* c) {
     PTB_CUDA(cudaGetLastError());
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->tree_info.aabb_sweeps = sweeps;
     c->tree_info.valid = valid;
     c->tree_info.depth = depth;
     c->tree_info.build_ms = ms;
     c->tree_info.list_n = c->list_n;
-    c->tree_info.list_overflow = c->list_overflow;
+    c->tree_info.trav_ploc = c->d_nodes_active == c->d_nodes2;
+    c->tree_info.trav_depth = c->tree_info.trav_ploc ? c->trav_depth : depth;
     c->tree_info.policy = ptb_effective_policy(c, c->traversal_request);
     return 0;
 }

@@ -54,6 +54,22 @@ struct DevCounters {
     unsigned int max_stack, pad;
 };
 
+// A frame covers the whole film, or -- render_tile (engine/path.py:96-118) -- one 64x64 window of it at (x0, y0); in window mode
+// every sample m of a pixel uses the SAME Sobol point with its own dimension rotation wanghash3(x, y, m) (path.py:115).
+struct FrameMap { int nx, ny, tiles_y, pps, x0, y0, window; };   // pps = path slots per sample (multiple of 32)
+__host__ __device__ inline FrameMap make_frame(int nx, int ny) {
+    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = 0; f.y0 = 0; f.window = 0;
+    int tx = (nx + 7) / 8; f.tiles_y = (ny + 3) / 4;
+    f.pps = tx * f.tiles_y * 32;
+    return f;
+}
+__host__ __device__ inline FrameMap make_window(int nx, int ny, int x0, int y0, int w, int h) {
+    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = x0; f.y0 = y0; f.window = 1;
+    int tx = (w + 7) / 8; f.tiles_y = (h + 3) / 4;
+    f.pps = tx * f.tiles_y * 32;
+    return f;
+}
+
 enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_ACCUM, ST_COUNT };
 
 struct StageEvent { int stage; cudaEvent_t a, b; };
@@ -106,7 +122,7 @@ struct ptb_ctx {
     float4 *d_tlo = nullptr, *d_thi = nullptr;   // [n] per leaf slot: inflated triangle bounds (w of tlo: PTB_TF_* flags)
     float4 *d_nlo = nullptr, *d_nhi = nullptr;   // [n-1] per internal node: traversal box (union of the unlisted leaves below)
     int32_t* d_list = nullptr;      // always-test list (leaf slots), PTB_LIST_CAP entries
-    int list_n = 0, list_overflow = 0;
+    int list_n = 0;
     int root_must = 0;
     float scene_abs = 0.0f;         // largest absolute coordinate of the reference root box and the traversal root box
     void* d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0;
@@ -149,6 +165,11 @@ struct ptb_ctx {
     int mlt_first = 0, mlt_count = 0;
     uint64_t mlt_seed = 0; uint32_t mlt_iter = 0;
     float mlt_lsp = 0.25f, mlt_sigma = 0.01f;
+
+    // ---- deferred Engine.render() calls (api.cu): consecutive one-sample calls are submitted as one wavefront batch ----
+    int pend_engine = -1, pend_first = 0, pend_count = 0;
+    bool coalesce = true;           // PTB_NO_COALESCE=1: submit every ptb_render call at once
+    int32_t* d_flags = nullptr;     // [4] device flags: [0] material id out of range in the loaded model
 };
 
 TraceScene ptb_trace_scene(const ptb_ctx* c);
@@ -161,13 +182,20 @@ int ptb_lbvh_build(ptb_ctx* c);
 // wavefront.cu
 int ptb_wf_init(ptb_ctx* c);
 int ptb_wf_upload_params(ptb_ctx* c);
-int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev);
+int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev, const int* window = nullptr);
+int ptb_wf_batch_capacity(const ptb_ctx* c);             // samples of the current film that fit one wavefront batch
+int ptb_wf_normaldist(ptb_ctx* c, const float* in_dev, int m, float* out_dev);
+int ptb_wf_check_mtlids(ptb_ctx* c, int nfaces);                    // flags material ids outside [-1, max_materials) in d_flags[0]
 int ptb_wf_sobol_points(ptb_ctx* c, int k_first, int count, int stride, float* P_dev);
 int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
 int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev, const float* dis_dev, int m, int policy, int anyhit,
                      int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
 int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
 int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev);
+// shade.cu
+int ptb_shade_fast_math(void);
+void ptb_shade_prepare_cache(ptb_ctx* c);
+void ptb_shade_launch(ptb_ctx* c, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
 int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
 int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails);
 int ptb_wf_mlt_reset(ptb_ctx* c);

@@ -157,16 +157,38 @@ PTB_D bool list_gate_ok(const TraceScene& S, const float4 (*s_gate)[2], int j, i
     float gl; bool gsure;
     return slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], ro, rd));
 }
-// One pass over the list: closest accepted triangle (ties: larger slot) into ret / best; ANYHIT: stop at the first one.  GATED = false
+// The list is scanned in two phases.  Phase 1 (list_candidates, uniform control flow: every lane looks at the same entry, broadcast
+// shared-memory reads, no branches): the conservative slab test of the entry's INFLATED bounds -- the leaf bound of ptb_traverse.cuh,
+// the same test a tree leaf gets from its parent's node step -- marks the entries whose triangle the ray can possibly be accepted by
+// (an ill-conditioned entry has no bound and is always marked).  Inside a room that is the two triangles of the wall the ray leaves
+// through, not all ten.  Phase 2 (list_scan): every lane walks its OWN marked entries (per-lane shared-memory index) with the exact
+// triangle test.  Before, all lanes ran the exact test on all entries, and its early exits (plane behind the ray, beyond the best hit)
+// left 20 of 32 lanes active in the long part.
+#ifndef PTB_LIST_FILTER
+#define PTB_LIST_FILTER 1           /* 0: every entry is a candidate (A/B builds) */
+#endif
+PTB_D unsigned list_candidates(const int* s_slot, const float4 (*s_box)[2], int nlist, int avoid_slot, const RayCons& R, const RayTrav& Q, float cull) {
+    unsigned cand = 0;
+    for (int j = 0; j < nlist; j++) {
+        const float4 lo = s_box[j][0], hi = s_box[j][1];
+        float lb;
+        const bool ok = !PTB_LIST_FILTER || (slab_trav(lo, hi, R, Q, &lb) && !(lb > cull));
+        const bool c = s_slot[j] != avoid_slot && (ok || (__float_as_int(lo.w) & PTB_TF_MUST) != 0);
+        cand |= c ? (1u << j) : 0u;
+    }
+    return cand;
+}
+// Closest accepted triangle among the marked entries (ties: larger slot) into ret / best; ANYHIT: stop at the first one.  GATED = false
 // leaves the gates out: the winner of the ungated pass is the winner of the gated one whenever its own gate passes (it is the
 // minimum over a superset), which the caller checks once per ray instead of once per candidate -- the gates of listed triangles are
 // boxes near the root, so the gated pass is a rare second pass.  *jw = list index of the winner.
 template <bool ANYHIT, bool GATED, bool COUNT>
-PTB_D bool list_scan(const TraceScene& S, const int* s_slot, const float4 (*s_tri)[4], const float4 (*s_gate)[2], int nlist, const RayIn& in, const RayCons& R,
+PTB_D bool list_scan(const TraceScene& S, const int* s_slot, const float4 (*s_tri)[4], const float4 (*s_gate)[2], unsigned cand, const RayIn& in, const RayCons& R,
                      HitRec& ret, float& best, int* jw, TraceCounters& C) {
-    for (int j = 0; j < nlist; j++) {
+    while (cand != 0u) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1u;
         const int slot = s_slot[j];
-        if (slot == in.avoid_slot) continue;
         Tri64 T; T.a = s_tri[j][0]; T.b = s_tri[j][1]; T.c = s_tri[j][2]; T.d = s_tri[j][3];
         if (COUNT) C.tris++;
         float dep, s, t;
@@ -194,11 +216,14 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
     __shared__ int s_slot[PTB_LIST_CAP];
     __shared__ float4 s_tri[PTB_LIST_CAP][4];
     __shared__ float4 s_gate[PTB_LIST_CAP][2];
+    __shared__ float4 s_box[PTB_LIST_CAP][2];          // inflated bounds (lo.w: PTB_TF_* flags)
     const int nlist = min(S.nlist, PTB_LIST_CAP);
     for (int j = threadIdx.x; j < nlist * 4; j += 256) {
         const int slot = S.list[j >> 2];
         s_tri[j >> 2][j & 3] = reinterpret_cast<const float4*>(S.tris + slot)[j & 3];
         if ((j & 3) < 2) s_gate[j >> 2][j & 3] = S.gbox[2 * slot + (j & 3)];
+        if ((j & 3) == 2) s_box[j >> 2][0] = S.tlo[slot];
+        if ((j & 3) == 3) s_box[j >> 2][1] = S.thi[slot];
         if ((j & 3) == 0) s_slot[j >> 2] = slot;
     }
     __syncthreads();
@@ -229,19 +254,21 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                 float best = ANYHIT ? fminf(in.tmax, PTB_INF) : PTB_INF;
                 const float best0 = best;
                 int jw = -1;
-                bool occluded = list_scan<ANYHIT, false, COUNT>(S, s_slot, s_tri, s_gate, nlist, in, R, ret, best, &jw, C);
+                delta = trav_delta(in.ro, S.scene_abs);
+                const RayTrav Q = ray_trav(R, delta);
+                const unsigned cand = list_candidates(s_slot, s_box, nlist, in.avoid_slot, R, Q, best + best * PTB_CULL_GUARD);
+                if (COUNT) C.boxes += nlist;
+                bool occluded = list_scan<ANYHIT, false, COUNT>(S, s_slot, s_tri, s_gate, cand, in, R, ret, best, &jw, C);
                 if (ret.hit && !list_gate_ok(S, s_gate, jw, ret.slot, R, in.ro, in.rd)) {
                     // the ungated winner is not a triangle the reference would have tested: start over, gate checked per candidate
                     ret.hit = 0; ret.depth = PTB_INF; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1; best = best0;
                     TraceCounters unused; unused.nodes = unused.boxes = unused.tris = 0; unused.max_stack = 0;
-                    occluded = list_scan<ANYHIT, true, false>(S, s_slot, s_tri, s_gate, nlist, in, R, ret, best, &jw, unused);
+                    occluded = list_scan<ANYHIT, true, false>(S, s_slot, s_tri, s_gate, cand, in, R, ret, best, &jw, unused);
                 }
                 // anything left in the tree?  its root box = union of the inflated bounds of every triangle not in the list
                 if (!occluded && S.n >= 2) {
                     float lb;
                     if (COUNT) C.boxes++;
-                    delta = trav_delta(in.ro, S.scene_abs);
-                    const RayTrav Q = ray_trav(R, delta);
                     live = S.nlo[0].x <= S.nhi[0].x && slab_trav(S.nlo[0], S.nhi[0], R, Q, &lb) && (S.root_must || !(lb > best + best * PTB_CULL_GUARD));
                 }
                 if (!live) {

@@ -24,6 +24,12 @@ struct __align__(16) Node64 { float4 a, b, c, d; };
 // whose computed depth obeys no bound: the child is never culled by distance
 #define PTB_NODE_MUST 0x40000000
 #define PTB_NODE_ID 0x3FFFFFFF
+// flags of a leaf slot (w of its inflated lower bound, lbvh.cu k_tri_prep): never hit (degenerate), ill-conditioned (no leaf bound:
+// bounded by its gate box, exempt from distance culling), big (candidate for the always-test list), on the always-test list
+#define PTB_TF_NEVER 1
+#define PTB_TF_MUST 2
+#define PTB_TF_BIG 4
+#define PTB_TF_LISTED 8
 // 64-byte packed triangle, indexed by sorted leaf slot:
 //   a = (v0.xyz, 1/D)  b = (u.xyz, uu)  c = (v.xyz, uv)  d = (n.xyz, vv)     u=v1-v0, v=v2-v0, n=u x v, D = uv*uv - uu*vv
 // Every field is the f32 expression geometries.py:121-141 evaluates per test (they depend on the triangle only), so
@@ -37,6 +43,8 @@ struct TraceScene {
     const int* __restrict__ slot_of;     // [n]  face id -> slot      (inverse of leaf, proper trees only)
     const int* __restrict__ gate;        // [n]  slot -> internal node whose child the leaf is (its box gates the triangle test)
     const float4* __restrict__ gbox;     // [2n] slot -> reference box (lo, hi) of its gate
+    const float4* __restrict__ tlo;      // [n]  slot -> inflated bounds of its triangle (lo.w: PTB_TF_* flags), hi
+    const float4* __restrict__ thi;
     const float4* __restrict__ nlo;      // [n-1] traversal boxes of the internal nodes (lo, hi); [0] = the root's
     const float4* __restrict__ nhi;
     float scene_abs;                     // largest absolute coordinate of the (inflated) scene bounds

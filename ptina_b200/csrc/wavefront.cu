@@ -19,99 +19,12 @@
 // generator state is carried.
 #include <cstdio>
 #include <cstdlib>
-#include "ptb_internal.h"
+#include "ptb_wavefront.cuh"
 #include "ptb_trace_kernel.cuh"
 
 namespace {
 
 constexpr int BLK = 128;
-
-// ---- pixel <-> path-slot mapping: a warp owns an 8x4 pixel tile so primary rays stay coherent -----------------
-struct FrameMap { int nx, ny, tiles_y, pps; };   // pps = path slots per sample (multiple of 32)
-__host__ __device__ inline FrameMap make_frame(int nx, int ny) {
-    FrameMap f; f.nx = nx; f.ny = ny;
-    int tx = (nx + 7) / 8; f.tiles_y = (ny + 3) / 4;
-    f.pps = tx * f.tiles_y * 32;
-    return f;
-}
-PTB_D bool slot_pixel(const FrameMap& f, int q, int* x, int* y) {
-    int tile = q >> 5, lane = q & 31;
-    int tx = tile / f.tiles_y, ty = tile - tx * f.tiles_y;
-    *x = tx * 8 + (lane >> 2);
-    *y = ty * 4 + (lane & 3);
-    return *x < f.nx && *y < f.ny;
-}
-
-// ---- random source: Sobol table of the path's sample (sobol.py:107-125) or the MLT chain vector (sampling/__init__.py:53-64)
-struct Rng {
-    const float* __restrict__ tab;
-    int base, dim;   // dim == 0 -> direct indexing (MLT)
-    PTB_D float draw(int c) const {
-        if (dim == 0) return tab[c];
-        int i = (int)((unsigned)base + (unsigned)c);   // i32 wrap of `self.i += 1`
-        return __ldg(&tab[pymod(i, dim)]);
-    }
-};
-// k consecutive draws starting at draw c0: one modulo, then increments with wrap-around (identical indices; the i32 wrap of
-// `self.i += 1` inside the run falls back to the per-draw modulo)
-struct RngRun {
-    const Rng& g; int i0, b0; bool fast;
-    PTB_D RngRun(const Rng& g_, int c0) : g(g_), i0(0), b0(0), fast(false) {
-        if (g.dim != 0) {
-            i0 = (int)((unsigned)g.base + (unsigned)c0);
-            fast = i0 <= 0x7fffffff - 16;
-            b0 = pymod(i0, g.dim);
-        } else i0 = c0;
-    }
-    PTB_D float draw(int j) const {     // j-th draw of the run, j < 16
-        if (g.dim == 0) return g.tab[i0 + j];
-        int b;
-        if (fast) { b = b0 + j; if (b >= g.dim) b -= g.dim; }
-        else b = pymod((int)((unsigned)i0 + (unsigned)j), g.dim);
-        return __ldg(&g.tab[b]);
-    }
-};
-
-// ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
-// returns the queue position reserved for this thread (-1 if !flag)
-template <int NT>
-PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
-    unsigned m = __ballot_sync(0xffffffffu, flag);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int rank = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) s_warp[w] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int i = 0; i < NT / 32; i++) { int c = s_warp[i]; s_warp[i] = tot; tot += c; }
-        *s_base = tot ? atomicAdd(counter, tot) : 0;
-    }
-    __syncthreads();
-    int pos = flag ? *s_base + s_warp[w] + rank : -1;
-    __syncthreads();
-    return pos;
-}
-
-// two queues at once (next extend queue + shadow queue): one 64-bit atomic per block on the adjacent counters (n_out, n_shadow)
-template <int NT>
-PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 * NT/32] */, unsigned long long* s_base, int* pa, int* pb) {
-    const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { s_warp[w] = __popc(ma); s_warp[NT / 32 + w] = __popc(mb); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int ta = 0, tb = 0;
-#pragma unroll
-        for (int i = 0; i < NT / 32; i++) { int c = s_warp[i]; s_warp[i] = ta; ta += c; c = s_warp[NT / 32 + i]; s_warp[NT / 32 + i] = tb; tb += c; }
-        *s_base = (ta | tb) ? atomicAdd(reinterpret_cast<unsigned long long*>(counter_pair), (unsigned long long)(unsigned)ta | ((unsigned long long)(unsigned)tb << 32)) : 0ull;
-    }
-    __syncthreads();
-    const unsigned long long base = *s_base;
-    *pa = fa ? (int)(unsigned)base + s_warp[w] + __popc(ma & ((1u << lane) - 1u)) : -1;
-    *pb = fb ? (int)(unsigned)(base >> 32) + s_warp[NT / 32 + w] + __popc(mb & ((1u << lane) - 1u)) : -1;
-    __syncthreads();
-}
 
 // ---- sampling/sobol.py:99-105 in closed form: X_k = XOR_{b in gray(k)} V[b+1];  P = X / 2^32 (sobol.py:19-29) ---------
 __global__ void k_sobol_points(const int* __restrict__ V, int dim, int k_first, int count, int stride, float* __restrict__ P) {
@@ -149,7 +62,8 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
             int x, y;
             if (slot_pixel(fm, q, &x, &y)) {
                 live = true;
-                Rng rng; rng.tab = sobolP + (size_t)s * dim; rng.base = wanghash2(x, y); rng.dim = dim;
+                Rng rng;
+                frame_rng(fm, sobolP, dim, s, x, y, &rng);
                 float dx = rng.draw(0), dy = rng.draw(1);
                 float fx = ((float)x + dx) / (float)fm.nx * 2.0f - 1.0f;
                 float fy = ((float)y + dy) / (float)fm.ny * 2.0f - 1.0f;
@@ -168,155 +82,6 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
         }
     }
     if (ctr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->paths, (unsigned long long)nsamp * fm.nx * fm.ny);
-}
-
-// ---- model.py:88-101 get_geometries + geometries.py:96-108 -------------------------------------------------------------------
-PTB_D void shading_frame(const float* __restrict__ verts, const int* __restrict__ mtlids, int f, float u, float v, V3 ro, V3 rd, float depth,
-                         V3* hitpos, V3* normal, float* tu, float* tv, int* mtlid) {
-    const float4* p = reinterpret_cast<const float4*>(verts + (size_t)f * 24);   // 3 corners x (pos3 nrm3 uv2) = 6 x float4
-    float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3), c0 = __ldg(p + 4), c1 = __ldg(p + 5);
-    float wx = 1.0f - u - v, wy = u, wz = v;
-    V3 n0 = mk3(a0.w, a1.x, a1.y), n1 = mk3(b0.w, b1.x, b1.y), n2 = mk3(c0.w, c1.x, c1.y);
-    V3 nrm = normalized(wx * n0 + wy * n1 + wz * n2);
-    *tu = wx * a1.z + wy * b1.z + wz * c1.z;
-    *tv = wx * a1.w + wy * b1.w + wz * c1.w;
-    *hitpos = ro + depth * rd;
-    float sg = -dot(rd, nrm);
-    if (sg < 0.0f) nrm = -nrm;
-    *normal = nrm;
-    *mtlid = __ldg(&mtlids[f]);
-}
-
-// ---- shade: the body of the while loop of path_trace (path.py:25-62) / BruteEngine.trace (brute.py:35-60) after the hit ---------
-// per-scene constants (materials without textures, light frames), recomputed whenever the parameters are uploaded
-__global__ void k_prepare_cache(const SceneParams* __restrict__ P, const float4* __restrict__ texels, SceneCache* SC) {
-    int i = threadIdx.x;
-    if (i <= PTB_MAX_MATERIALS) {
-        int mtlid = i == PTB_MAX_MATERIALS ? -1 : i;
-        bool plain = true;
-        if (mtlid >= 0) for (int s = 0; s < PTB_NSLOTS; s++) plain = plain && P->mat_tex[mtlid][s] == -1;
-        SC->plain[i] = plain;
-        if (plain) SC->mat[i] = material_get(P, texels, mtlid, 0.0f, 0.0f);
-    }
-    if (i <= PTB_MAX_LIGHTS) SC->light[i] = light_cache(P->lights[i]);
-}
-
-// 1024 threads per SM at 64 registers; the block size sets how many warps run the same instruction stream (the kernel is
-// ~130 KB of SASS: with many small blocks at different places of it the instruction caches thrash, ncu `stall_no_inst`)
-#ifndef PTB_SHADE_BLK
-#define PTB_SHADE_BLK 512
-#endif
-constexpr int SBLK = PTB_SHADE_BLK;
-template <int ENGINE>
-__global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
-                                               const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
-                                               FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
-    __shared__ int s_warp[SBLK / 32]; __shared__ int s_base;
-    __shared__ int s_warp2[2 * (SBLK / 32)]; __shared__ unsigned long long s_base2;
-    const int count = ctrl->n_in;
-    const int rounded = (count + SBLK - 1) / SBLK * SBLK;
-    for (int i0 = blockIdx.x * SBLK; i0 < rounded; i0 += gridDim.x * SBLK) {
-        int idx = i0 + threadIdx.x;
-        bool alive = false, want_shadow = false;
-        int p = -1, avoid_slot = -1;
-        V3 next_o = v3s(0.0f), next_d = v3s(0.0f), sh_dir = v3s(0.0f), sh_contrib = v3s(0.0f);
-        float sh_dis = 0.0f;
-        if (idx < count) {
-            {   // start the next iteration's records on their way
-                const int nxt = idx + gridDim.x * SBLK;
-                if (nxt < count) { asm volatile("prefetch.global.L1 [%0];" ::"l"(q_in.o + nxt)); asm volatile("prefetch.global.L1 [%0];" ::"l"(q_in.d + nxt)); }
-            }
-            float4 o4 = q_in.o[idx], d4 = q_in.d[idx];
-            p = __float_as_int(o4.w);
-            float4 h4 = st.hit[p], t4 = st.thr[p], r4 = st.result[p];
-            V3 ro = mk3(o4.x, o4.y, o4.z), rd = mk3(d4.x, d4.y, d4.z);
-            V3 thr = mk3(t4.x, t4.y, t4.z), result = mk3(r4.x, r4.y, r4.z);
-            float last_pdf = r4.w;
-            int depth = __float_as_int(t4.w) + 1;                       // path.py:26 depth += 1
-            int hit_index = __float_as_int(h4.w);
-            bool hit = hit_index >= 0;
-            Rng rng;
-            if (dim == 0) { rng.tab = rngtab + (size_t)p * rng_stride; rng.base = 0; rng.dim = 0; }
-            else {
-                int s = p / fm.pps, q = p - s * fm.pps, x, y;
-                slot_pixel(fm, q, &x, &y);
-                rng.tab = rngtab + (size_t)s * dim; rng.base = wanghash2(x, y); rng.dim = dim;
-            }
-            // path.py:31-35 / brute.py:41-43
-            LitHit lit = light_hit_cached(P, SC, ro, rd);
-            if (lit.hit != 0 && (!hit || lit.dis < h4.x)) {
-                if (ENGINE == PTB_ENGINE_PATH) {
-                    float mis = power_heuristic(last_pdf, lit.pdf);
-                    result = result + thr * (mis * lit.color);
-                } else {
-                    result = result + thr * lit.color;
-                }
-            }
-            if (!hit) {
-                result = result + thr * world_at(P, texels, rd);        // path.py:37-39
-            } else {
-                avoid_slot = __ldg(&slot_of[hit_index]);
-                V3 hitpos, normal; float tu, tv; int mtlid;
-                shading_frame(verts, mtlids, hit_index, h4.y, h4.z, ro, rd, h4.x, &hitpos, &normal, &tu, &tv, &mtlid);
-                const int mslot = mtlid < 0 ? PTB_MAX_MATERIALS : mtlid;
-                Disney mat;
-                if (SC->plain[mslot]) mat = SC->mat[mslot];              // untextured: precomputed with the same arithmetic
-                else mat = material_get(P, texels, mtlid, tu, tv);
-                float sign = -dot(rd, normal);                            // path.py:44-46 (recomputed on the flipped normal)
-                if (sign < 0.0f) normal = -normal;
-                V3 wi = -rd;
-                int c0;
-                const RngRun run(rng, ENGINE == PTB_ENGINE_PATH ? 2 + 6 * (depth - 1) : 2 + 3 * (depth - 1));
-                if (ENGINE == PTB_ENGINE_PATH) {
-                    c0 = 0;
-                    // path.py:48-56 next-event estimation
-                    V3 ls = mk3(run.draw(c0), run.draw(c0 + 1), run.draw(c0 + 2));
-                    LitSample li = light_sample_cached(P, SC, hitpos, ls);
-                    if (any_gt(li.color, 0.0f)) {
-                        V3 brdf_clr = disney_brdf(mat, normal, sign, wi, li.dir);
-                        float brdf_pdf = vavg(brdf_clr);                  // sic: path.py:53
-                        float mis = power_heuristic(li.pdf, brdf_pdf);
-                        V3 direct = mis * li.color * brdf_clr * dot_or_zero(normal, li.dir);
-                        V3 contrib = thr * direct;
-                        // a contribution that is exactly zero (light sample below the horizon, black throughput) adds nothing whether or
-                        // not the shadow ray is blocked, so the ray is not traced; NaNs compare unequal and still go through
-                        if (!(contrib.x == 0.0f && contrib.y == 0.0f && contrib.z == 0.0f)) {
-                            sh_dir = li.dir; sh_dis = li.dis; sh_contrib = contrib;
-                            want_shadow = true;
-                        }
-                    }
-                    c0 += 3;
-                } else {
-                    c0 = 0;
-                }
-                // path.py:58-62 / brute.py:56-60
-                BSDFSample bs = disney_bounce(mat, normal, sign, wi, mk3(run.draw(c0), run.draw(c0 + 1), run.draw(c0 + 2)));
-                thr = thr * bs.color;
-                last_pdf = bs.pdf;                                         // path.py:61
-                st.thr[p] = make_float4(thr.x, thr.y, thr.z, __int_as_float(depth));
-                // loop condition path.py:25 / brute.py:35
-                if (ENGINE == PTB_ENGINE_PATH) alive = depth < 5 && any_gt(thr, 0.0f) && any_ne0(bs.outdir);
-                else alive = depth < 5 && any_gt(thr, PTB_EPS);
-                next_o = hitpos;
-                if (alive) next_d = normalized(bs.outdir);                 // path.py:28  r.d = r.d.normalized() at the top of the next iteration
-            }
-            st.result[p] = make_float4(result.x, result.y, result.z, last_pdf);
-        }
-        int pos, ps = -1;
-        if (ENGINE == PTB_ENGINE_PATH) block_append2<SBLK>(alive, want_shadow, &ctrl->n_out, s_warp2, &s_base2, &pos, &ps);
-        else pos = block_append<SBLK>(alive, &ctrl->n_out, s_warp, &s_base);
-        if (alive) {
-            q_out.o[pos] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
-            q_out.d[pos] = make_float4(next_d.x, next_d.y, next_d.z, __int_as_float(avoid_slot));   // avoid = hit.index (as its leaf slot)
-        }
-        if (ENGINE == PTB_ENGINE_PATH) {
-            if (want_shadow) {
-                q_shadow.o[ps] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
-                q_shadow.d[ps] = make_float4(sh_dir.x, sh_dir.y, sh_dir.z, sh_dis);
-                q_shadow.c[ps] = make_float4(sh_contrib.x, sh_contrib.y, sh_contrib.z, __int_as_float(avoid_slot));
-            }
-        }
-    }
 }
 
 // ---- preview.py:23-41: primary hit -> albedo into pass 1, shading normal into pass 2 ---------------------------------------------
@@ -412,51 +177,6 @@ __global__ void __launch_bounds__(BLK) k_gather_primary(FrameMap fm, PathState s
         if (depth) depth[pix] = h.x;
         if (index) index[pix] = id;
         if (uv) { uv[2 * pix] = h.y; uv[2 * pix + 1] = h.z; }
-    }
-}
-
-PTB_D Disney disney_from(const float* p) {
-    Disney m;
-    m.basecolor = mk3(p[0], p[1], p[2]); m.metallic = p[3]; m.roughness = p[4]; m.specular = p[5]; m.specularTint = p[6];
-    m.subsurface = p[7]; m.sheen = p[8]; m.sheenTint = p[9]; m.clearcoat = p[10]; m.clearcoatGloss = p[11]; m.transmission = p[12]; m.ior = p[13];
-    disney_init(m);
-    return m;
-}
-// what: 0 eval_bsdf, 1 sample_bsdf, 2 material_get, 3 light_hit, 4 light_sample, 5 world_at
-__global__ void __launch_bounds__(BLK) k_shade_tap(const SceneParams* __restrict__ P, const float4* __restrict__ texels, int what, const float* __restrict__ in0,
-                                                   const float* __restrict__ in1, const int* __restrict__ ini, int m, float* __restrict__ out) {
-    int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= m) return;
-    if (what == 0 || what == 1) {
-        Disney d = disney_from(in0 + 14 * i);
-        const float* g = in1 + 10 * i;
-        V3 nrm = mk3(g[0], g[1], g[2]), wi = mk3(g[4], g[5], g[6]), x = mk3(g[7], g[8], g[9]);
-        if (what == 0) {
-            V3 r = disney_brdf(d, nrm, g[3], wi, x);
-            out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
-        } else {
-            BSDFSample s = disney_bounce(d, nrm, g[3], wi, x);
-            float* o = out + 7 * i;
-            o[0] = s.outdir.x; o[1] = s.outdir.y; o[2] = s.outdir.z; o[3] = s.pdf; o[4] = s.color.x; o[5] = s.color.y; o[6] = s.color.z;
-        }
-    } else if (what == 2) {
-        Disney d = material_get(P, texels, ini[i], in0[2 * i], in0[2 * i + 1]);
-        float* o = out + 14 * i;
-        o[0] = d.basecolor.x; o[1] = d.basecolor.y; o[2] = d.basecolor.z; o[3] = d.metallic; o[4] = d.roughness; o[5] = d.specular; o[6] = d.specularTint;
-        o[7] = d.subsurface; o[8] = d.sheen; o[9] = d.sheenTint; o[10] = d.clearcoat; o[11] = d.clearcoatGloss; o[12] = d.transmission; o[13] = d.ior;
-    } else if (what == 3) {
-        const float* r = in0 + 6 * i;
-        LitHit l = light_hit(P, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]));
-        float* o = out + 6 * i;
-        o[0] = (float)l.hit; o[1] = l.dis; o[2] = l.pdf; o[3] = l.color.x; o[4] = l.color.y; o[5] = l.color.z;
-    } else if (what == 4) {
-        const float* r = in0 + 6 * i;
-        LitSample l = light_sample(P, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]));
-        float* o = out + 8 * i;
-        o[0] = l.dis; o[1] = l.dir.x; o[2] = l.dir.y; o[3] = l.dir.z; o[4] = l.pdf; o[5] = l.color.x; o[6] = l.color.y; o[7] = l.color.z;
-    } else {
-        V3 c = world_at(P, texels, mk3(in0[3 * i], in0[3 * i + 1], in0[3 * i + 2]));
-        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
     }
 }
 
@@ -583,6 +303,16 @@ __global__ void __launch_bounds__(256) k_selftest_div(int what, long long n, uns
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(fails, bad);
 }
 
+__global__ void __launch_bounds__(BLK) k_normaldist_tap(const float* __restrict__ in, int m, float* __restrict__ out) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i < m) out[i] = normaldist(in[i]);
+}
+__global__ void __launch_bounds__(256) k_check_mtlids(const int* __restrict__ mtlids, int n, int max_materials, int* flag) {
+    bool bad = false;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) { const int m = mtlids[i]; bad = bad || m < -1 || m >= max_materials; }
+    if (bad) *flag = 1;
+}
+
 inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 
 }  // namespace
@@ -700,8 +430,7 @@ int ptb_wf_upload_params(ptb_ctx* c) {
     c->h_params.nx = c->nx; c->h_params.ny = c->ny;
     // pageable host source: the copy is staged before the call returns, so later host edits cannot race it
     PTB_CUDA(cudaMemcpyAsync(c->d_params, &c->h_params, sizeof(SceneParams), cudaMemcpyHostToDevice, c->stream));
-    k_prepare_cache<<<1, 128, 0, c->stream>>>(c->d_params, c->d_texels, c->d_cache);
-    c->launches++;
+    ptb_shade_prepare_cache(c);
     c->params_dirty = false;
     return 0;
 }
@@ -745,10 +474,8 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
             c->launches++;
         }
         ptb_stage_begin(c, ST_SHADE);
-        k_shade<ENGINE><<<c->sm_count * (1024 / SBLK), SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
-                                                            c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
+        ptb_shade_launch(c, ENGINE, rngtab, dim, rng_stride, fm, cur, st);
         ptb_stage_end(c);
-        c->launches += 1;
         if (ENGINE == PTB_ENGINE_PATH) {
             if (overlap) {
                 PTB_CUDA(cudaEventRecord(c->ev_shade, st));
@@ -771,13 +498,15 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     return 0;
 }
 
-int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev) {
+// window: NULL = the whole film, `count` Sobol points k_first, k_first+stride, ...; else {x0, y0, w, h} = `count` samples of every pixel of
+// that window, all at Sobol point k_first (render_tile, engine/path.py:96-118)
+int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev, const int* window) {
     if (c->nx <= 0 || c->ny <= 0) { ptb_set_error("film size not set (ptb_set_size)"); return 1; }
     if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
     if (ptb_wf_upload_params(c)) return 1;
     cudaStream_t st = c->stream;
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
-    FrameMap fm = make_frame(c->nx, c->ny);
+    FrameMap fm = window ? make_window(c->nx, c->ny, window[0], window[1], window[2], window[3]) : make_frame(c->nx, c->ny);
 
     if (engine == PTB_ENGINE_MLT) {
         if (c->mlt_count <= 0) { ptb_set_error("MLT chains not initialised (ptb_mlt_reset)"); return 1; }
@@ -801,13 +530,14 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
     }
 
     int per_batch = (int)(c->max_paths / fm.pps);
+    if (window && count > per_batch) { ptb_set_error("a window of %d samples needs %lld path slots, pool has %lld", count, (long long)count * fm.pps, (long long)c->max_paths); return 1; }
     if (per_batch < 1) { ptb_set_error("film %dx%d needs %d path slots per sample, pool has %lld", c->nx, c->ny, fm.pps, (long long)c->max_paths); return 1; }
     if (sample_out_dev) count = 1;
     for (int done = 0; done < count; done += per_batch) {
         int ns = count - done < per_batch ? count - done : per_batch;
         if (ensure_sobolP(c, ns)) return 1;
         ptb_stage_begin(c, ST_RAYGEN);
-        if (ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
+        if (window ? ptb_wf_sobol_points(c, k_first, 1, 1, c->d_sobolP) : ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
         k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
         k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, engine != PTB_ENGINE_PREVIEW, c->st, c->xq[0], c->d_ctrl, ctr);
         ptb_stage_end(c);
@@ -876,17 +606,28 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
     return 0;
 }
 
-int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev) {
-    if (ptb_wf_upload_params(c)) return 1;
-    k_shade_tap<<<nblk(m), BLK, 0, c->stream>>>(c->d_params, c->d_texels, what, in0_dev, in1_dev, ini_dev, m, out_dev);
+int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev) {
+    const float4* film = c->d_film + (size_t)pass * c->caps.max_filmsize;
+    k_resolve<<<nblk((long long)c->nx * c->ny), BLK, 0, c->stream>>>(film, c->nx, c->ny, mode, out_dev);
     c->launches++;
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
 
-int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev) {
-    const float4* film = c->d_film + (size_t)pass * c->caps.max_filmsize;
-    k_resolve<<<nblk((long long)c->nx * c->ny), BLK, 0, c->stream>>>(film, c->nx, c->ny, mode, out_dev);
+int ptb_wf_batch_capacity(const ptb_ctx* c) {
+    if (c->nx <= 0 || c->ny <= 0) return 1;
+    const long long cap = c->max_paths / make_frame(c->nx, c->ny).pps;
+    return cap < 1 ? 1 : (int)cap;
+}
+int ptb_wf_normaldist(ptb_ctx* c, const float* in_dev, int m, float* out_dev) {
+    k_normaldist_tap<<<nblk(m), BLK, 0, c->stream>>>(in_dev, m, out_dev);
+    c->launches++;
+    PTB_CUDA(cudaGetLastError());
+    return 0;
+}
+int ptb_wf_check_mtlids(ptb_ctx* c, int nfaces) {
+    int grid = nblk(nfaces, 256); if (grid > c->sm_count * 8) grid = c->sm_count * 8;
+    k_check_mtlids<<<grid, 256, 0, c->stream>>>(c->d_mtlids, nfaces, c->caps.max_materials, c->d_flags);
     c->launches++;
     PTB_CUDA(cudaGetLastError());
     return 0;

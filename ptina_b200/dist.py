@@ -37,6 +37,33 @@ def reduce_film(film, dst=0, group=None):
     return film
 
 
-def reduce_film_pass(id=0, dst=0):
-    """In-place reduce of the native film pass onto rank dst (ordered on torch's current stream)."""
-    return reduce_film(_native.context().film_tensor(id), dst)
+_staging = {}
+
+
+def reduce_film_pass(id=0, dst=0, group=None):
+    """Sum film pass `id` of every rank onto rank `dst`, OUT OF PLACE: each rank's own film keeps only its own samples, so the call
+    is idempotent -- render more, reduce again, and nothing is counted twice (an in-place reduce would leave rank dst's film holding
+    everybody's samples and re-add them on the next call).  Returns the summed film [nx*ny, 4] on rank dst (a staging tensor that the
+    next call reuses) and None elsewhere.  Ordered on torch's current stream."""
+    return reduce_out_of_place(_native.context().film_tensor(id), dst, group)
+
+
+def reduce_out_of_place(film, dst=0, group=None):
+    """The out-of-place reduce of reduce_film_pass on any tensor (CPU tensors in the gloo tests)."""
+    key = (film.device, tuple(film.shape))
+    buf = _staging.get(key)
+    if buf is None:
+        _staging.clear()
+        buf = _staging[key] = torch.empty_like(film)
+    buf.copy_(film)
+    reduce_film(buf, dst, group)
+    return buf if (not dist.is_initialized() or dist.get_rank(group) == dst) else None
+
+
+def resolve(total):
+    """filmtable.py:47-63 on a reduced film [nx*ny, 4] -> image [nx, ny, 4] (rgb / w, a = 1; magenta where w == 0)."""
+    nx, ny = _native.context().get_size()
+    w = total[:, 3:4]
+    img = torch.where(w != 0, torch.cat([total[:, :3] / w, torch.ones_like(w)], 1),
+                      torch.tensor([0.9, 0.4, 0.9, 0.0], device=total.device).expand_as(total))
+    return img.reshape(nx, ny, 4)

@@ -13,3 +13,5 @@ class BruteEngine(metaclass=Singleton):
 
     render = PathEngine.render
     render_range = PathEngine.render_range
+    render_tile = PathEngine.render_tile
+    render_final = PathEngine.render_final

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ptina_b200.dist import shard_range, reduce_film
+from ptina_b200.dist import shard_range, reduce_film, reduce_out_of_place
 
 
 def test_shard_range_partitions():
@@ -33,9 +33,19 @@ def _worker(rank, world, port, out):
         g = torch.Generator().manual_seed(k)
         film[:, :3] += torch.rand(nx * ny, 3, generator=g)
         film[:, 3] += 1
-    reduce_film(film, dst=0)
+    # out of place, twice (a frame, more samples, a second frame): the per-rank film must keep only its own samples
+    total = reduce_out_of_place(film, dst=0)
+    own = film.clone()
+    total2 = reduce_out_of_place(film, dst=0)
+    assert torch.equal(film, own)
     if rank == 0:
-        torch.save(film, out)
+        assert torch.equal(total2, total)
+        torch.save(total.clone(), out)
+    else:
+        assert total is None and total2 is None
+    reduce_film(film, dst=0)          # the in-place primitive still sums onto dst
+    if rank == 0:
+        assert torch.allclose(film, torch.load(out), rtol=1e-6, atol=1e-6)
     dist.barrier()
     dist.destroy_process_group()
 

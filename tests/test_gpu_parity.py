@@ -41,7 +41,7 @@ def test_lbvh_bit_exact(gpu, name):
     for key in ('bmin', 'bmax'):
         assert np.array_equal(bits(a[key]), bits(b[key])), f'{name}: {key} differs'
     assert info.valid == 1 and info.depth == o.validate_tree() and info.policy == _native.TRAVERSE_ORDERED
-    assert info.list_overflow == 0 and info.list_n == {'cornell_boxes': 10, 'cornell_monkey': 10}.get(name, info.list_n)
+    assert info.list_n == {'cornell_boxes': 10, 'cornell_monkey': 10}.get(name, info.list_n)
 
 
 @pytest.mark.parametrize('name', list(SMALL))
@@ -303,7 +303,7 @@ def test_triangle_soup_matches_reference_order(gpu, kind):
     a, b = gpu.export_tree(), o.export_tree()
     for key in ('mc', 'id', 'leaf', 'child'):
         assert np.array_equal(a[key], b[key])
-    assert info.list_n == {'few_big': 6, 'many_big': 32, 'no_big': 0}[kind] and info.list_overflow == 0
+    assert info.list_n == {'few_big': 6, 'many_big': 32, 'no_big': 0}[kind]
     tri = verts[:, :3].reshape(nf, 3, 3)
     m = 30000
     f = rng.integers(0, nf, m)
