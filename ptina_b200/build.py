@@ -22,7 +22,9 @@ NVCC_FLAGS = NVCC_BASE + STRICT
 
 
 def flags_for(src, fast_shade):
-    return NVCC_BASE + (FAST if (fast_shade and src == 'shade.cu') else STRICT)
+    if fast_shade and src == 'shade.cu':
+        return NVCC_BASE + (list(fast_shade) if isinstance(fast_shade, (list, tuple)) else FAST)
+    return NVCC_BASE + STRICT
 
 
 def _nvcc():
@@ -77,4 +79,5 @@ if __name__ == '__main__':
     defs = [a[2:] for a in sys.argv if a.startswith('-D')]
     outs = [a[6:] for a in sys.argv if a.startswith('--out=')]
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None,
-                fast_shade=True if '--fast-shade' in sys.argv else None))
+                fast_shade=([f for a in sys.argv if a.startswith('--shade-flags=') for f in a[14:].split(',')] + ['-DPTB_SHADE_FAST=1']) if any(a.startswith('--shade-flags=') for a in sys.argv)
+                else (True if '--fast-shade' in sys.argv else None)))

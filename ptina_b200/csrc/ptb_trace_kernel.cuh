@@ -315,6 +315,20 @@ PTB_D void ld_qnode256(const uint4* p, uint4* a, uint4* b) {
                  : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w) : "l"(p));
 }
 
+// 64-byte triangle record of a big tree (global-memory variant): two 256-bit loads that do not allocate in L1 -- a ray tests ~2 leaf
+// triangles out of a million, so the line is not coming back, and the L1 is better spent on the top levels of the node array
+#ifndef PTB_STREAM_TRIS
+#define PTB_STREAM_TRIS 1
+#endif
+PTB_D Tri64 ld_tri_stream(const Tri64* p) {
+    Tri64 T;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(T.a.x), "=f"(T.a.y), "=f"(T.a.z), "=f"(T.a.w), "=f"(T.b.x), "=f"(T.b.y), "=f"(T.b.z), "=f"(T.b.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(T.c.x), "=f"(T.c.y), "=f"(T.c.z), "=f"(T.c.w), "=f"(T.d.x), "=f"(T.d.y), "=f"(T.d.z), "=f"(T.d.w) : "l"(reinterpret_cast<const char*>(p) + 32));
+    return T;
+}
+
 #define PTB_PQ 4                    /* pending-leaf ring entries per lane */
 #ifndef PTB_VOTE_N
 #define PTB_VOTE_N 1                /* node step iff PTB_VOTE_N * (lanes ready for one) > PTB_VOTE_L * (lanes with a pending leaf) */
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                 const int slot = s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
                 q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
                 if (!(lnear > cull)) {
-                    const Tri64 T = S.tris[slot];
+                    const Tri64 T = (!SMEM && PTB_STREAM_TRIS) ? ld_tri_stream(S.tris + slot) : S.tris[slot];
                     if (COUNT) C.tris++;
                     float dep, s, t;
                     if (tri_fast(T, R.o, R.d, best, &dep, &s, &t)) {

@@ -175,6 +175,7 @@ def test_unmodified_benchmark_script(gpu, tmp_path, capsys, monkeypatch):
     os.symlink(os.path.join(root, 'assets'), tmp_path / 'assets')
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(compat.PATH)
+    gpu.sobol_reset()                      # a fresh process would start here (SobolSampler.reset(): 64 updates)
     ns = compat.run_script(str(script))
     out = capsys.readouterr().out
     assert '31 samples...' in out and out.strip().endswith('sps')

@@ -674,8 +674,9 @@ def test_preview_engine_passes(gpu):
 
 
 def test_native_library_is_what_ran(gpu, native_so):
+    import os
     maps = open('/proc/self/maps').read()
-    assert 'libptina_b200.so' in maps
+    assert os.path.basename(os.environ.get('PTINA_B200_LIB', 'libptina_b200.so')) in maps
     assert gpu.launches() > 0
 
 
