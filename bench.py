@@ -373,9 +373,9 @@ class Bench:
         sc = self.scenes.metropolis()
         self.load(dict(sc, engine='path'))
         nch = 1 << 18
-        per = nch // self.world
-        eng = MLTPathEngine(nchains=nch, seed=0, chains=(self.rank * per, per))
-        eng.chains = (self.rank * per, per)
+        first, per = self.pdist.shard_chains(nch, self.rank, self.world)
+        eng = MLTPathEngine(nchains=nch, seed=0, chains=(first, per))
+        eng.chains = (first, per)
         eng.reset()
         ctx = self.ctx
         self.worker.clear()

@@ -101,6 +101,8 @@ static void release_ctx(ptb_ctx* c) {
     if (c->ev_shade) cudaEventDestroy(c->ev_shade);
     if (c->ev_shadow) cudaEventDestroy(c->ev_shadow);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (cudaEvent_t e : {c->ev_shade1, c->ev_shadow1, c->ev_fork, c->ev_join}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {c->stream3, c->stream4}) if (st) cudaStreamDestroy(st);
     delete c;
 }
 

@@ -70,6 +70,17 @@ __host__ __device__ inline FrameMap make_window(int nx, int ny, int x0, int y0, 
     return f;
 }
 
+// A lane = one wavefront in flight: its queues, control block, streams and events.  Lane 0 is the context's own (whole pools, the
+// caller's stream); lane 1 works in the upper half of every pool on streams of its own, so two independent populations of paths
+// (the two halves of the MLT chains) can be on the device at once -- each fills the SMs the other's small kernels leave idle.
+struct Ctrl;
+struct Lane {
+    RayQueue xq[2]; RayQueue sq; ExpQ tq, tq2;
+    Ctrl* ctrl = nullptr;
+    cudaStream_t s_main = nullptr, s_side = nullptr;
+    cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
+};
+
 enum { ST_RAYGEN = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_ACCUM, ST_COUNT };
 
 struct StageEvent { int stage; cudaEvent_t a, b; };
@@ -145,6 +156,9 @@ struct ptb_ctx {
     ExpQ tq2{};                     // second tree queue: the shadow stage of bounce b runs beside the extend stage of bounce b+1
     cudaStream_t stream2 = nullptr; // non-blocking side stream of the shadow stage
     cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
+    cudaStream_t stream3 = nullptr, stream4 = nullptr;            // lane 1: main and side stream
+    cudaEvent_t ev_shade1 = nullptr, ev_shadow1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    bool mlt_two_lanes = true;      // PTB_MLT_ONE_LANE=1: the whole chain population as one wavefront
     bool overlap_shadow = true;     // PTB_NO_OVERLAP=1 turns the overlap off
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
@@ -195,7 +209,8 @@ int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev);
 // shade.cu
 int ptb_shade_fast_math(void);
 void ptb_shade_prepare_cache(ptb_ctx* c);
-void ptb_shade_launch(ptb_ctx* c, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
+void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
+Lane ptb_lane(ptb_ctx* c, int which);
 int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
 int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails);
 int ptb_wf_mlt_reset(ptb_ctx* c);

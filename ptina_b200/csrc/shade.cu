@@ -206,14 +206,14 @@ void ptb_shade_prepare_cache(ptb_ctx* c) {
     c->launches++;
 }
 
-void ptb_shade_launch(ptb_ctx* c, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
+void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
     const int grid = c->sm_count * (1024 / SBLK);
     if (engine == PTB_ENGINE_PATH)
         k_shade<PTB_ENGINE_PATH><<<grid, SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
-                                                     c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
+                                                     L.xq[cur], L.xq[cur ^ 1], L.sq, L.ctrl);
     else
         k_shade<PTB_ENGINE_BRUTE><<<grid, SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
-                                                      c->xq[cur], c->xq[cur ^ 1], c->sq, c->d_ctrl);
+                                                      L.xq[cur], L.xq[cur ^ 1], L.sq, L.ctrl);
     c->launches++;
 }
 

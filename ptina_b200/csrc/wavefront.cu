@@ -238,10 +238,12 @@ __global__ void __launch_bounds__(BLK) k_mlt_reset(float* Xold, float4* Lold, in
     for (int j = 0; j < 32; j++) Xold[(size_t)i * 32 + j] = g.next();
 }
 // mltpath.py:56-74: mutate, then camera ray from the first two dims
-__global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restrict__ P, const float* __restrict__ Xold, float* __restrict__ Xnew, int nchains, int chain_first,
+// chains [first, first + nchains) of this process's population (one lane's share); path slot = chain index, queue position = local index
+__global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restrict__ P, const float* __restrict__ Xold, float* __restrict__ Xnew, int first, int nchains, int chain_first,
                                                     uint64_t seed, uint32_t iter, float lsp, float sigma, PathState st, RayQueue xq, Ctrl* ctrl, DevCounters* ctr) {
-    int i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= nchains) return;
+    const int q = blockIdx.x * BLK + threadIdx.x;
+    if (q >= nchains) return;
+    const int i = first + q;
     Philox g; g.init(seed, (uint32_t)(chain_first + i), iter);
     const float* xo = Xold + (size_t)i * 32; float* xn = Xnew + (size_t)i * 32;
     if (g.next() < lsp) { for (int j = 0; j < 32; j++) xn[j] = g.next(); }
@@ -251,15 +253,16 @@ __global__ void __launch_bounds__(BLK) k_mlt_raygen(const SceneParams* __restric
     st.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));
     st.result[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     rd = normalized(rd);                                                                // path.py:28
-    xq.o[i] = make_float4(ro.x, ro.y, ro.z, __int_as_float(i));
-    xq.d[i] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));
-    if (i == 0) { ctrl->n_in = nchains; if (ctr) atomicAdd(&ctr->paths, (unsigned long long)nchains); }
+    xq.o[q] = make_float4(ro.x, ro.y, ro.z, __int_as_float(i));
+    xq.d[q] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));
+    if (q == 0) { ctrl->n_in = nchains; if (ctr) atomicAdd(&ctr->paths, (unsigned long long)nchains); }
 }
 // mltpath.py:47-52 splat + 75-81 accept/reject
 __global__ void __launch_bounds__(BLK) k_mlt_finish(float* __restrict__ Xold, const float* __restrict__ Xnew, float4* __restrict__ Lold, const float4* __restrict__ result,
-                                                    int nchains, int chain_first, uint64_t seed, uint32_t iter, int nx, int ny, float4* __restrict__ film) {
+                                                    int first, int nchains, int chain_first, uint64_t seed, uint32_t iter, int nx, int ny, float4* __restrict__ film) {
     int i = blockIdx.x * BLK + threadIdx.x;
     if (i >= nchains) return;
+    i += first;
     float4 Ln4 = result[i], Lo4 = Lold[i];
     V3 Ln = mk3(Ln4.x, Ln4.y, Ln4.z), Lo = mk3(Lo4.x, Lo4.y, Lo4.z);
     float AL_new = vavg(Ln) + 1e-10f, AL_old = vavg(Lo) + 1e-10f;
@@ -329,7 +332,7 @@ int ptb_tree_mode(const ptb_ctx* c, int n) {
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
 // which: 0 = extend, 1 = shadow / taps (selects the tree-queue counters of the control block, reset by k_ctrl_*)
 template <class IO>
-static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int which, int* cursor, const int* count_ptr, cudaStream_t st, const ExpQ& tq) {
+static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int policy, int which, int* cursor, const int* count_ptr, cudaStream_t st, const ExpQ& tq, Ctrl* ctrl) {
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     if (policy == PTB_TRAVERSE_REFERENCE || S.n < 2) {
         if (c->counting) k_trace_simple<IO, 0, true><<<c->blocks_ref, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
@@ -338,7 +341,7 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
         if (c->counting) k_trace_simple<IO, 1, true><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
         else k_trace_simple<IO, 1, false><<<c->blocks_exact, PTB_TRACE_BLK, 0, st>>>(S, io, cursor, count_ptr, ctr);
     } else {
-        int* n_tree = &c->d_ctrl->n_tree[which]; int* cur_tree = &c->d_ctrl->cur_tree[which];
+        int* n_tree = &ctrl->n_tree[which]; int* cur_tree = &ctrl->cur_tree[which];
         // phase A: per-ray setup, always-test list, root test; survivors -> tree queue
         if (c->counting) k_trace_pre<IO, true><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, tq, n_tree, ctr);
         else k_trace_pre<IO, false><<<c->blocks_generic, 256, 0, st>>>(S, io, count_ptr, tq, n_tree, ctr);
@@ -362,11 +365,23 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
     }
     c->launches++;
 }
-static void launch_extend(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr) {
-    launch_trace_io(c, S, ExtendIO{q.o, q.d, c->st.hit}, policy, 0, cursor, count_ptr, c->stream, c->tq);
+static void launch_extend(ptb_ctx* c, const Lane& L, const TraceScene& S, int policy, const RayQueue& q) {
+    launch_trace_io(c, S, ExtendIO{q.o, q.d, c->st.hit}, policy, 0, &L.ctrl->cur_extend, &L.ctrl->n_in, L.s_main, L.tq, L.ctrl);
 }
-static void launch_shadow(ptb_ctx* c, const TraceScene& S, int policy, const RayQueue& q, int* cursor, const int* count_ptr, cudaStream_t st, const ExpQ& tq) {
-    launch_trace_io(c, S, ShadowIO{q.o, q.d, q.c, c->st.result}, policy, 1, cursor, count_ptr, st, tq);
+static void launch_shadow(ptb_ctx* c, const Lane& L, const TraceScene& S, int policy, cudaStream_t st, const ExpQ& tq) {
+    launch_trace_io(c, S, ShadowIO{L.sq.o, L.sq.d, L.sq.c, c->st.result}, policy, 1, &L.ctrl->cur_shadow, &L.ctrl->n_shadow, st, tq, L.ctrl);
+}
+// lane 0: the context's pools and streams; lane 1: the upper half of every pool, streams 3 / 4, the second control block
+Lane ptb_lane(ptb_ctx* c, int which) {
+    Lane L;
+    const size_t off = which ? (size_t)(c->max_paths / 2) : 0;
+    for (int k = 0; k < 2; k++) { L.xq[k].o = c->xq[k].o + off; L.xq[k].d = c->xq[k].d + off; L.xq[k].c = nullptr; }
+    L.sq.o = c->sq.o + off; L.sq.d = c->sq.d + off; L.sq.c = c->sq.c + off;
+    for (int k = 0; k < PTB_EXP_K; k++) { L.tq.e[k] = c->tq.e[k] + off; L.tq2.e[k] = c->tq2.e[k] + off; }
+    L.ctrl = c->d_ctrl + which;
+    L.s_main = which ? c->stream3 : c->stream; L.s_side = which ? c->stream4 : c->stream2;
+    L.ev_shade = which ? c->ev_shade1 : c->ev_shade; L.ev_shadow = which ? c->ev_shadow1 : c->ev_shadow;
+    return L;
 }
 
 void ptb_stage_begin(ptb_ctx* c, int stage) {
@@ -402,8 +417,8 @@ int ptb_wf_init(ptb_ctx* c) {
                        &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->tq.e[0], &c->tq.e[1], &c->tq.e[2], &c->tq.e[3], &c->tq.e[4],
                        &c->tq2.e[0], &c->tq2.e[1], &c->tq2.e[2], &c->tq2.e[3], &c->tq2.e[4]};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
-    PTB_CUDA(cudaMalloc(&c->d_ctrl, sizeof(Ctrl)));
-    PTB_CUDA(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
+    PTB_CUDA(cudaMalloc(&c->d_ctrl, 2 * sizeof(Ctrl)));          // one control block per lane
+    PTB_CUDA(cudaMemset(c->d_ctrl, 0, 2 * sizeof(Ctrl)));
     PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
@@ -417,6 +432,10 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shadow, cudaEventDisableTiming));
+    PTB_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    PTB_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_shade1, &c->ev_shadow1, &c->ev_fork, &c->ev_join}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    c->mlt_two_lanes = getenv("PTB_MLT_ONE_LANE") == nullptr;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
@@ -454,11 +473,10 @@ static int ensure_sobolP(ptb_ctx* c, int nsamp) {
 
 // bounce loop shared by every engine: extend -> shade -> shadow, up to 5 times (path.py:25)
 template <int ENGINE>
-static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride, FrameMap fm) {
+static int run_bounces(ptb_ctx* c, const Lane& L, const float* rngtab, int dim, int rng_stride, FrameMap fm) {
     TraceScene S = ptb_trace_scene(c);
     int policy = ptb_effective_policy(c, c->traversal_request);
-    DevCounters* ctr = c->counting ? c->d_counters : nullptr;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = L.s_main;
     int cur = 0;
     // The shadow stage of bounce b and the extend stage of bounce b+1 are independent (shadow rays add into `result`, which extend
     // never touches; shade of b+1 waits for both), so they run on two streams: each fills the SMs the other leaves idle while its
@@ -466,34 +484,34 @@ static int run_bounces(ptb_ctx* c, const float* rngtab, int dim, int rng_stride,
     const bool overlap = ENGINE == PTB_ENGINE_PATH && c->overlap_shadow && !c->profiling;
     for (int depth = 1; depth <= 5; depth++) {
         ptb_stage_begin(c, ST_EXTEND);
-        launch_extend(c, S, policy, c->xq[cur], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
+        launch_extend(c, L, S, policy, L.xq[cur]);
         ptb_stage_end(c);
         if (overlap && depth > 1) {
-            PTB_CUDA(cudaStreamWaitEvent(st, c->ev_shadow, 0));           // the previous shadow stage is done with sq / result
-            k_ctrl_reset_shadow<<<1, 1, 0, st>>>(c->d_ctrl);
+            PTB_CUDA(cudaStreamWaitEvent(st, L.ev_shadow, 0));           // the previous shadow stage is done with sq / result
+            k_ctrl_reset_shadow<<<1, 1, 0, st>>>(L.ctrl);
             c->launches++;
         }
         ptb_stage_begin(c, ST_SHADE);
-        ptb_shade_launch(c, ENGINE, rngtab, dim, rng_stride, fm, cur, st);
+        ptb_shade_launch(c, L, ENGINE, rngtab, dim, rng_stride, fm, cur, st);
         ptb_stage_end(c);
         if (ENGINE == PTB_ENGINE_PATH) {
             if (overlap) {
-                PTB_CUDA(cudaEventRecord(c->ev_shade, st));
-                PTB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_shade, 0));
-                launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow, c->stream2, c->tq2);
-                PTB_CUDA(cudaEventRecord(c->ev_shadow, c->stream2));
+                PTB_CUDA(cudaEventRecord(L.ev_shade, st));
+                PTB_CUDA(cudaStreamWaitEvent(L.s_side, L.ev_shade, 0));
+                launch_shadow(c, L, S, policy, L.s_side, L.tq2);
+                PTB_CUDA(cudaEventRecord(L.ev_shadow, L.s_side));
             } else {
                 ptb_stage_begin(c, ST_SHADOW);
-                launch_shadow(c, S, policy, c->sq, &c->d_ctrl->cur_shadow, &c->d_ctrl->n_shadow, st, c->tq);
+                launch_shadow(c, L, S, policy, st, L.tq);
                 ptb_stage_end(c);
             }
         }
-        if (overlap) k_ctrl_next_extend<<<1, 1, 0, st>>>(c->d_ctrl);
-        else k_ctrl_next<<<1, 1, 0, st>>>(c->d_ctrl);
+        if (overlap) k_ctrl_next_extend<<<1, 1, 0, st>>>(L.ctrl);
+        else k_ctrl_next<<<1, 1, 0, st>>>(L.ctrl);
         c->launches++;
         cur ^= 1;
     }
-    if (overlap) PTB_CUDA(cudaStreamWaitEvent(st, c->ev_shadow, 0));
+    if (overlap) PTB_CUDA(cudaStreamWaitEvent(st, L.ev_shadow, 0));
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -510,25 +528,37 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
 
     if (engine == PTB_ENGINE_MLT) {
         if (c->mlt_count <= 0) { ptb_set_error("MLT chains not initialised (ptb_mlt_reset)"); return 1; }
+        // The chains are independent of each other from one render() to the next, and a wavefront of 2^18 paths leaves the persistent
+        // kernels mostly tail: the population runs as two halves on two lanes (own queues, control block and streams), which only
+        // meet again when the call returns.  Splats are atomic, chain state is per chain: nothing is shared but the film.
+        const int n = c->mlt_count;
+        const bool two = c->mlt_two_lanes && !c->profiling && n >= 8192 && (long long)n <= c->max_paths;
+        const int nlanes = two ? 2 : 1;
+        if (two) { PTB_CUDA(cudaEventRecord(c->ev_fork, st)); PTB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0)); }
         for (int it = 0; it < count; it++) {
-            int n = c->mlt_count;
-            ptb_stage_begin(c, ST_RAYGEN);
-            k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
-            k_mlt_raygen<<<nblk(n), BLK, 0, st>>>(c->d_params, c->d_Xold, c->d_Xnew, n, c->mlt_first, c->mlt_seed, c->mlt_iter, c->mlt_lsp, c->mlt_sigma,
-                                                  c->st, c->xq[0], c->d_ctrl, ctr);
-            ptb_stage_end(c);
-            c->launches += 2;
-            if (run_bounces<PTB_ENGINE_PATH>(c, c->d_Xnew, 0, 32, fm)) return 1;
-            ptb_stage_begin(c, ST_ACCUM);
-            k_mlt_finish<<<nblk(n), BLK, 0, st>>>(c->d_Xold, c->d_Xnew, c->d_Lold, c->st.result, n, c->mlt_first, c->mlt_seed, c->mlt_iter, c->nx, c->ny, c->d_film);
-            ptb_stage_end(c);
-            c->launches++;
+            for (int w = 0; w < nlanes; w++) {
+                const Lane L = ptb_lane(c, w);
+                const int first = w == 0 ? 0 : n / 2, cnt = two ? (w == 0 ? n / 2 : n - n / 2) : n;
+                ptb_stage_begin(c, ST_RAYGEN);
+                k_ctrl_begin<<<1, 1, 0, L.s_main>>>(L.ctrl, 0);
+                k_mlt_raygen<<<nblk(cnt), BLK, 0, L.s_main>>>(c->d_params, c->d_Xold, c->d_Xnew, first, cnt, c->mlt_first, c->mlt_seed, c->mlt_iter, c->mlt_lsp, c->mlt_sigma,
+                                                              c->st, L.xq[0], L.ctrl, ctr);
+                ptb_stage_end(c);
+                c->launches += 2;
+                if (run_bounces<PTB_ENGINE_PATH>(c, L, c->d_Xnew, 0, 32, fm)) return 1;
+                ptb_stage_begin(c, ST_ACCUM);
+                k_mlt_finish<<<nblk(cnt), BLK, 0, L.s_main>>>(c->d_Xold, c->d_Xnew, c->d_Lold, c->st.result, first, cnt, c->mlt_first, c->mlt_seed, c->mlt_iter, c->nx, c->ny, c->d_film);
+                ptb_stage_end(c);
+                c->launches++;
+            }
             c->mlt_iter++;
         }
+        if (two) { PTB_CUDA(cudaEventRecord(c->ev_join, c->stream3)); PTB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0)); }
         PTB_CUDA(cudaGetLastError());
         return 0;
     }
 
+    const Lane L0 = ptb_lane(c, 0);
     int per_batch = (int)(c->max_paths / fm.pps);
     if (window && count > per_batch) { ptb_set_error("a window of %d samples needs %lld path slots, pool has %lld", count, (long long)count * fm.pps, (long long)c->max_paths); return 1; }
     if (per_batch < 1) { ptb_set_error("film %dx%d needs %d path slots per sample, pool has %lld", c->nx, c->ny, fm.pps, (long long)c->max_paths); return 1; }
@@ -538,15 +568,15 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
         if (ensure_sobolP(c, ns)) return 1;
         ptb_stage_begin(c, ST_RAYGEN);
         if (window ? ptb_wf_sobol_points(c, k_first, 1, 1, c->d_sobolP) : ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
-        k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
-        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, engine != PTB_ENGINE_PREVIEW, c->st, c->xq[0], c->d_ctrl, ctr);
+        k_ctrl_begin<<<1, 1, 0, st>>>(L0.ctrl, 0);
+        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, engine != PTB_ENGINE_PREVIEW, c->st, L0.xq[0], L0.ctrl, ctr);
         ptb_stage_end(c);
         c->launches += 2;
         if (engine == PTB_ENGINE_PREVIEW) {
             TraceScene S = ptb_trace_scene(c);
             int policy = ptb_effective_policy(c, c->traversal_request);
             ptb_stage_begin(c, ST_EXTEND);
-            launch_extend(c, S, policy, c->xq[0], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
+            launch_extend(c, L0, S, policy, L0.xq[0]);
             ptb_stage_end(c);
             ptb_stage_begin(c, ST_ACCUM);
             size_t pass = (size_t)c->caps.max_filmsize;
@@ -555,8 +585,8 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
             c->launches += 1;
             continue;
         }
-        int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, c->d_sobolP, c->sobol_dim, 0, fm)
-                                           : run_bounces<PTB_ENGINE_BRUTE>(c, c->d_sobolP, c->sobol_dim, 0, fm);
+        int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, L0, c->d_sobolP, c->sobol_dim, 0, fm)
+                                           : run_bounces<PTB_ENGINE_BRUTE>(c, L0, c->d_sobolP, c->sobol_dim, 0, fm);
         if (rc) return 1;
         ptb_stage_begin(c, ST_ACCUM);
         k_accumulate<<<nblk(fm.pps), BLK, 0, st>>>(c->d_film, c->st.result, fm, ns, sample_out_dev);
@@ -575,14 +605,15 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
     if (fm.pps > c->max_paths) { ptb_set_error("film larger than the path pool"); return 1; }
     if (ensure_sobolP(c, 1)) return 1;
     if (ptb_wf_sobol_points(c, k, 1, 1, c->d_sobolP)) return 1;
-    k_ctrl_begin<<<1, 1, 0, st>>>(c->d_ctrl, 0);
-    k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, 1, c->st, c->xq[0], c->d_ctrl, nullptr);
+    const Lane L0 = ptb_lane(c, 0);
+    k_ctrl_begin<<<1, 1, 0, st>>>(L0.ctrl, 0);
+    k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, 1, c->st, L0.xq[0], L0.ctrl, nullptr);
     if (rays_dev) k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, rays_dev, nullptr, nullptr, nullptr, nullptr, 0);
     if (hit_dev || depth_dev || index_dev || uv_dev) {
         if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
         TraceScene S = ptb_trace_scene(c);
         int policy = ptb_effective_policy(c, c->traversal_request);
-        launch_extend(c, S, policy, c->xq[0], &c->d_ctrl->cur_extend, &c->d_ctrl->n_in);
+        launch_extend(c, L0, S, policy, L0.xq[0]);
         k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, nullptr, hit_dev, depth_dev, index_dev, uv_dev, 1);
     }
     c->launches += 4;
@@ -600,8 +631,8 @@ int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev
     c->launches += 2;
     int eff = ptb_effective_policy(c, policy);
     int* cur = &c->d_ctrl->pad[1]; const int* cnt = &c->d_ctrl->pad[0];
-    if (anyhit) launch_trace_io(c, S, TapIO<true>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq);
-    else launch_trace_io(c, S, TapIO<false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq);
+    if (anyhit) launch_trace_io(c, S, TapIO<true>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq, c->d_ctrl);
+    else launch_trace_io(c, S, TapIO<false>{c->sq.o, c->sq.d, c->sq.c, hit_dev, depth_dev, index_dev, uv_dev}, eff, 1, cur, cnt, c->stream, c->tq, c->d_ctrl);
     PTB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -18,6 +18,14 @@ def shard_range(k_first, count, rank, world):
     return k_first + rank, mine, world
 
 
+def shard_chains(nchains, rank, world):
+    """Contiguous split of the MLT chains (engine/mltpath.py:12: 2^18 of them): -> (first, count); every chain on exactly one rank.
+    Chain c draws from the Philox stream keyed (seed, c, iteration) wherever it runs, so the split does not change what a chain does."""
+    base, extra = divmod(nchains, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
 def render_sharded(engine, nsamples, rank=None, world=None):
     """Every rank calls this with the same arguments; advances the Sobol time by `nsamples` on all ranks."""
     ctx = _native.context()

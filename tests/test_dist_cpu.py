@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ptina_b200.dist import shard_range, reduce_film, reduce_out_of_place
+from ptina_b200.dist import shard_range, shard_chains, reduce_film, reduce_out_of_place
 
 
 def test_shard_range_partitions():
@@ -19,6 +19,15 @@ def test_shard_range_partitions():
             assert sorted(got) == list(range(65, 65 + count))
             sizes = [shard_range(65, count, r, world)[1] for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_chains_partitions():
+    for world in (1, 2, 3, 4, 8):
+        for n in (1, 7, 2**14, 2**18):
+            parts = [shard_chains(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+            assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
 
 
 def _worker(rank, world, port, out):
@@ -43,6 +52,18 @@ def _worker(rank, world, port, out):
         torch.save(total.clone(), out)
     else:
         assert total is None and total2 is None
+    # MLT sharding (mltpath.py:47-52 splats): every chain adds (L, 1) at its own pixel; chains are split over the ranks
+    nch = 1000
+    first, cnt = shard_chains(nch, rank, world)
+    splat = torch.zeros(nx * ny, 4)
+    for c in range(first, first + cnt):
+        g = torch.Generator().manual_seed(10_000 + c)
+        px = int(torch.randint(0, nx * ny, (1,), generator=g))
+        splat[px, :3] += torch.rand(3, generator=g)
+        splat[px, 3] += 1
+    tot = reduce_out_of_place(splat, dst=0)
+    if rank == 0:
+        torch.save(tot.clone(), out + '.mlt')
     reduce_film(film, dst=0)          # the in-place primitive still sums onto dst
     if rank == 0:
         assert torch.allclose(film, torch.load(out), rtol=1e-6, atol=1e-6)
@@ -61,3 +82,11 @@ def test_gloo_film_reduce_world2(tmp_path):
         want[:, :3] += torch.rand(48, 3, generator=g)
         want[:, 3] += 1
     assert torch.allclose(film, want, rtol=1e-6, atol=1e-6) and torch.equal(film[:, 3], want[:, 3])
+    mlt = torch.load(out + '.mlt')
+    want = torch.zeros(48, 4)
+    for c in range(1000):
+        g = torch.Generator().manual_seed(10_000 + c)
+        px = int(torch.randint(0, 48, (1,), generator=g))
+        want[px, :3] += torch.rand(3, generator=g)
+        want[px, 3] += 1
+    assert torch.allclose(mlt, want, rtol=1e-5, atol=1e-6) and torch.equal(mlt[:, 3], want[:, 3]) and mlt[:, 3].sum() == 1000
