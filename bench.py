@@ -526,6 +526,13 @@ def run_gpu(args):
             r = B.measure_pt(workload(args, name), 'weak', steps_small, 2, stages=True)
             r.pop('_raw')
             configs[key] = r
+        # config 2 in PTB_MODE_FAST (opt-in, NON-parity: approximate division / FMA contraction in the shading stage only)
+        ctx.set_mode('fast')
+        r = B.measure_pt(workload(args, 'cornell_monkey'), 'weak', steps_small, 2, stages=True, check=False)
+        r.pop('_raw')
+        r['note'] = 'non-parity mode (ptb_set_mode PTB_MODE_FAST): holds the 1e-3 image gate, not the 1e-5 BSDF tap gate; not the headline'
+        configs['config2_fast_mode_nonparity'] = r
+        ctx.set_mode('parity')
         # config 2, strong: ONE 32-spp frame split over the N GPUs
         if world > 1:
             s2 = workload(args, 'cornell_monkey')

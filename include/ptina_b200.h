@@ -42,6 +42,12 @@ enum { PTB_TRAVERSE_AUTO = 0,      /* ordered + culled when the tree validates, 
        PTB_TRAVERSE_ORDERED = 2,   /* near-first, distance-culled; conservative box tests + exact gate test on acceptance */
        PTB_TRAVERSE_ORDERED_EXACT = 3 /* the same order with the exact (division-equivalent) slab test at every node */ };
 
+/* PTB_MODE_PARITY (default): every stage in strict IEEE binary32 -- bit-exact trees / rays / hits, BSDF eval / pdf within 1e-5 of the
+ * reference.  PTB_MODE_FAST (opt-in, the role tree/middlebvh.py's "fast, non-parity" path plays in the reference): the shading stage
+ * runs its FMA-contracted, approximate-division build; trees, rays and hit ids are unchanged, shaded values agree to ~1e-4 per tap and
+ * to the 1e-3 image gate. */
+enum { PTB_MODE_PARITY = 0, PTB_MODE_FAST = 1 };
+
 /* things.py:12-19 init_things(...) capacities.  Zero fields take the reference defaults. */
 typedef struct ptb_caps {
     int32_t max_faces;      /* 2^21 */
@@ -84,6 +90,8 @@ int ptb_version(void);
 int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out);
 int ptb_destroy(ptb_ctx* ctx);
 int ptb_set_stream(ptb_ctx* ctx, void* cuda_stream);
+int ptb_set_mode(ptb_ctx* ctx, int mode);                           /* PTB_MODE_*; PTB_FAST=1 in the environment makes FAST the default */
+int ptb_get_mode(ptb_ctx* ctx, int* mode);
 int ptb_synchronize(ptb_ctx* ctx);                                  /* worker.py:17-18 */
 int ptb_flush(ptb_ctx* ctx);                                        /* submit recorded ptb_render calls without waiting */
 

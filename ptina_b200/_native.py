@@ -16,6 +16,7 @@ HOST, DEVICE = 0, 1
 ENGINE_PATH, ENGINE_BRUTE, ENGINE_PREVIEW, ENGINE_MLT = 0, 1, 2, 3
 LIGHT_TYPES = {'POINT': 1, 'AREA': 2}            # light/__init__.py:11
 TRAVERSE_AUTO, TRAVERSE_REFERENCE, TRAVERSE_ORDERED, TRAVERSE_ORDERED_EXACT = 0, 1, 2, 3
+MODE_PARITY, MODE_FAST = 0, 1
 
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -42,7 +43,7 @@ class Counters(ctypes.Structure):
 
 # every symbol include/ptina_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_synchronize', 'ptb_flush',
+    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_set_mode', 'ptb_get_mode', 'ptb_synchronize', 'ptb_flush',
     'ptb_set_sobol_table', 'ptb_sobol_reset', 'ptb_sobol_get_time', 'ptb_sobol_set_time', 'ptb_sobol_point',
     'ptb_load_model', 'ptb_load_materials', 'ptb_load_images', 'ptb_clear_lights', 'ptb_add_light', 'ptb_set_world_light',
     'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_export_traversal', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
@@ -154,6 +155,17 @@ class Context:
 
     def synchronize(self):
         self._check(self.L.ptb_synchronize(self.h))
+
+    def set_mode(self, mode):
+        """MODE_PARITY (default) or MODE_FAST / 'fast': the shading stage's FMA-contracted, approximate-division build (non-parity)."""
+        mode = {'parity': MODE_PARITY, 'fast': MODE_FAST}.get(mode, mode)
+        self._check(self.L.ptb_set_mode(self.h, int(mode)))
+
+    @property
+    def mode(self):
+        m = ctypes.c_int()
+        self._check(self.L.ptb_get_mode(self.h, ctypes.byref(m)))
+        return m.value
 
     def flush(self):
         """Submit the render() calls recorded so far (they are merged into wavefront batches) without waiting for the device."""

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(HERE, 'libptina_b200.so')
-SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu', 'shade.cu']
+SOURCES = ['api.cu', 'lbvh.cu', 'wavefront.cu', 'shade.cu', 'shade.cu:fast']      # shade.cu is compiled twice (strict / fast), see its header
 HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh', 'ptb_trace_kernel.cuh', 'ptb_wavefront.cuh', '../../include/ptina_b200.h']
 
 # -fmad=false / -prec-div / -prec-sqrt / -ftz=false: IEEE binary32 in source order -- what makes Morton codes, primary
@@ -15,15 +15,15 @@ HEADERS = ['ptb_internal.h', 'ptb_math.cuh', 'ptb_shade.cuh', 'ptb_traverse.cuh'
 NVCC_BASE = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-ftz=false',
              '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '--expt-relaxed-constexpr']
 STRICT = ['-fmad=false', '-prec-div=true', '-prec-sqrt=true']
-# shade.cu only, and only on request (`--fast-shade` / PTB_FAST_SHADE=1): FMA contraction, approximate division and square root in the
-# arithmetic that owes the reference 1e-5, not bits (see the header of csrc/shade.cu).  Not the default: DESIGN.md section 6 has the numbers.
+# the second compilation of shade.cu (PTB_MODE_FAST): FMA contraction, approximate division and square root in the arithmetic that
+# owes the reference 1e-5 / an image gate, not bits
 FAST = ['-fmad=true', '-prec-div=false', '-prec-sqrt=false', '-DPTB_SHADE_FAST=1']
 NVCC_FLAGS = NVCC_BASE + STRICT
 
 
-def flags_for(src, fast_shade):
-    if fast_shade and src == 'shade.cu':
-        return NVCC_BASE + (list(fast_shade) if isinstance(fast_shade, (list, tuple)) else FAST)
+def flags_for(src, fast_flags=None):
+    if src.endswith(':fast'):
+        return NVCC_BASE + (list(fast_flags) if fast_flags else FAST)
     return NVCC_BASE + STRICT
 
 
@@ -38,15 +38,13 @@ def stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    files = [os.path.join(CSRC, f.split(':')[0]) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force=False, verbose=False, defines=(), out=None, fast_shade=None):
+def build(force=False, verbose=False, defines=(), out=None, fast_flags=None):
     """defines / out: tuning variants (`-DNAME=value` ... into another .so, selected at run time with PTINA_B200_LIB)."""
-    if fast_shade is None:
-        fast_shade = os.environ.get('PTB_FAST_SHADE', '0') == '1'
-    if not force and not stale() and not defines and out is None and not fast_shade:
+    if not force and not stale() and not defines and out is None and not fast_flags:
         return SO
     out = out or SO
     tag = '' if out == SO else '_' + os.path.basename(out).replace('.so', '')
@@ -60,8 +58,8 @@ def build(force=False, verbose=False, defines=(), out=None, fast_shade=None):
     procs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', tag + '.o'))
-        cmd = [nvcc] + ccbin + flags_for(src, fast_shade) + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(HERE, 'build', src.replace('.cu:fast', '_fast.cu').replace('.cu', tag + '.o'))
+        cmd = [nvcc] + ccbin + flags_for(src, fast_flags) + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src.split(':')[0]), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:
@@ -78,6 +76,6 @@ def build(force=False, verbose=False, defines=(), out=None, fast_shade=None):
 if __name__ == '__main__':
     defs = [a[2:] for a in sys.argv if a.startswith('-D')]
     outs = [a[6:] for a in sys.argv if a.startswith('--out=')]
+    fast = [f for a in sys.argv if a.startswith('--fast-flags=') for f in a[13:].split(',')]      # tuning: other flags for the fast build of shade.cu
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else None,
-                fast_shade=([f for a in sys.argv if a.startswith('--shade-flags=') for f in a[14:].split(',')] + ['-DPTB_SHADE_FAST=1']) if any(a.startswith('--shade-flags=') for a in sys.argv)
-                else (True if '--fast-shade' in sys.argv else None)))
+                fast_flags=(fast + ['-DPTB_SHADE_FAST=1']) if fast else None))

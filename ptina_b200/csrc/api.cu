@@ -157,6 +157,7 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
     PTB_CUDA(cudaMemset(c->d_flags, 0, 16));
     if (ptb_wf_init(c)) { release_ctx(c); return 1; }
     c->coalesce = getenv("PTB_NO_COALESCE") == nullptr;
+    c->fast_shade = getenv("PTB_FAST") != nullptr && getenv("PTB_FAST")[0] == '1';
     // defaults of the reference singletons
     memset(&c->h_params, 0, sizeof c->h_params);
     for (int k = 0; k < 4; k++) c->h_params.world_fac[k] = 0.1f;       // light/world.py:14-16 (tex field zero-initialised)
@@ -180,6 +181,13 @@ int ptb_destroy(ptb_ctx* c) {
 
 int ptb_set_stream(ptb_ctx* c, void* s) { CHECK_FLUSH(c); c->stream = (cudaStream_t)s; return 0; }
 int ptb_flush(ptb_ctx* c) { CHECK_FLUSH(c); return 0; }
+int ptb_set_mode(ptb_ctx* c, int mode) {
+    CHECK_FLUSH(c);
+    if (mode != PTB_MODE_PARITY && mode != PTB_MODE_FAST) { ptb_set_error("unknown mode %d", mode); return 1; }
+    if (c->fast_shade != (mode == PTB_MODE_FAST)) { c->fast_shade = mode == PTB_MODE_FAST; c->params_dirty = true; }   // the per-scene cache is recomputed by the build in use
+    return 0;
+}
+int ptb_get_mode(ptb_ctx* c, int* mode) { CHECK_CTX(c); *mode = c->fast_shade ? PTB_MODE_FAST : PTB_MODE_PARITY; return 0; }
 int ptb_synchronize(ptb_ctx* c) {
     CHECK_FLUSH(c);
     DeviceGuard g(c->device);

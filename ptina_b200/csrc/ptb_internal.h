@@ -183,6 +183,7 @@ struct ptb_ctx {
     // ---- deferred Engine.render() calls (api.cu): consecutive one-sample calls are submitted as one wavefront batch ----
     int pend_engine = -1, pend_first = 0, pend_count = 0;
     bool coalesce = true;           // PTB_NO_COALESCE=1: submit every ptb_render call at once
+    bool fast_shade = false;        // PTB_MODE_FAST: the shading stage compiled with FMA contraction and approximate division (shade.cu)
     int32_t* d_flags = nullptr;     // [4] device flags: [0] material id out of range in the loaded model
 };
 
@@ -204,12 +205,21 @@ int ptb_wf_sobol_points(ptb_ctx* c, int k_first, int count, int stride, float* P
 int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
 int ptb_wf_intersect(ptb_ctx* c, const float* rays_dev, const int32_t* avoid_dev, const float* dis_dev, int m, int policy, int anyhit,
                      int32_t* hit_dev, float* depth_dev, int32_t* index_dev, float* uv_dev);
-int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
 int ptb_wf_resolve(ptb_ctx* c, int pass, int mode, float* out_dev);
-// shade.cu
-int ptb_shade_fast_math(void);
-void ptb_shade_prepare_cache(ptb_ctx* c);
-void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
+// shade.cu, compiled twice (strict / fast arithmetic); the dispatchers below pick by c->fast_shade
+void ptb_shade_prepare_cache_strict(ptb_ctx* c);
+void ptb_shade_prepare_cache_fast(ptb_ctx* c);
+void ptb_shade_launch_strict(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
+void ptb_shade_launch_fast(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st);
+int ptb_wf_shade_tap_strict(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
+int ptb_wf_shade_tap_fast(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev);
+inline int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev) {
+    return c->fast_shade ? ptb_wf_shade_tap_fast(c, what, in0_dev, in1_dev, ini_dev, m, out_dev) : ptb_wf_shade_tap_strict(c, what, in0_dev, in1_dev, ini_dev, m, out_dev);
+}
+inline void ptb_shade_prepare_cache(ptb_ctx* c) { c->fast_shade ? ptb_shade_prepare_cache_fast(c) : ptb_shade_prepare_cache_strict(c); }
+inline void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
+    c->fast_shade ? ptb_shade_launch_fast(c, L, engine, rngtab, dim, rng_stride, fm, cur, st) : ptb_shade_launch_strict(c, L, engine, rngtab, dim, rng_stride, fm, cur, st);
+}
 Lane ptb_lane(ptb_ctx* c, int which);
 int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
 int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails);

@@ -1,11 +1,14 @@
 // shade.cu -- the shading stage of the wavefront (and its parity taps): everything between two traversal stages of a path.
 //
-// Own translation unit so that its floating-point contract can be chosen apart from the traversal's.  The traversal, the LBVH build,
-// ray generation and the film (lbvh.cu, wavefront.cu) owe the reference BITS and are compiled -fmad=false -prec-div=true
-// -prec-sqrt=true.  Shading owes it 1e-5 (BSDF eval / pdf) and 1e-3 on converged images: by default it is compiled the same way;
-// build.py's `fast_shade` switch compiles THIS file with FMA contraction and approximate division / square root instead
-// (PTB_SHADE_FAST is defined then).  What must not move stays explicit either way: the hit position that becomes the next ray's
-// origin (shading_frame) is written with __fmul_rn / __fadd_rn.
+// Own translation unit because it is compiled TWICE into the library (ptina_b200/build.py):
+//   strict (default, PTB_MODE_PARITY): -fmad=false -prec-div=true -prec-sqrt=true like the traversal, the LBVH build, ray generation
+//          and the film (lbvh.cu, wavefront.cu), which owe the reference BITS.  Shading owes it 1e-5 per BSDF eval / pdf, and holds it.
+//   fast   (opt-in, PTB_MODE_FAST, -DPTB_SHADE_FAST): FMA contraction, approximate division and square root.  Measured on config 2: the
+//          shade stage 2.58 -> 1.95 ms (frame 7.85 -> 7.22 ms, almost all of it from division / square root: FMA alone gives 2.46 ms);
+//          the converged-image gate (rel-RMSE <= 1e-3 at 1024 spp) still holds, the 1e-5 tap gate does NOT (sampled directions move by
+//          up to 1e-4 where sqrt(1 - h^2) cancels), which is why it is a mode and not the default.
+// What must not move stays explicit either way: the hit position that becomes the next ray's origin (shading_frame) is written with
+// __fmul_rn / __fadd_rn.
 #include "ptb_wavefront.cuh"
 
 namespace {
@@ -193,20 +196,18 @@ inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
 
 }  // namespace
 
-int ptb_shade_fast_math(void) {
 #ifdef PTB_SHADE_FAST
-    return 1;
+#define SHADE_FN(name) name##_fast
 #else
-    return 0;
+#define SHADE_FN(name) name##_strict
 #endif
-}
 
-void ptb_shade_prepare_cache(ptb_ctx* c) {
+void SHADE_FN(ptb_shade_prepare_cache)(ptb_ctx* c) {
     k_prepare_cache<<<1, 128, 0, c->stream>>>(c->d_params, c->d_texels, c->d_cache);
     c->launches++;
 }
 
-void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
+void SHADE_FN(ptb_shade_launch)(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
     const int grid = c->sm_count * (1024 / SBLK);
     if (engine == PTB_ENGINE_PATH)
         k_shade<PTB_ENGINE_PATH><<<grid, SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
@@ -217,7 +218,7 @@ void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab
     c->launches++;
 }
 
-int ptb_wf_shade_tap(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev) {
+int SHADE_FN(ptb_wf_shade_tap)(ptb_ctx* c, int what, const float* in0_dev, const float* in1_dev, const int32_t* ini_dev, int m, float* out_dev) {
     if (ptb_wf_upload_params(c)) return 1;
     k_shade_tap<<<nblk(m), BLK, 0, c->stream>>>(c->d_params, c->d_texels, what, in0_dev, in1_dev, ini_dev, m, out_dev);
     c->launches++;

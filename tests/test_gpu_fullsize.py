@@ -64,6 +64,32 @@ def test_converged_image_gate_1024spp(gpu, name):
     assert 0.9 * int(g['rays']) <= cnt['rays'] <= 1.001 * int(g['rays'])
 
 
+def test_fast_mode_holds_the_image_gate_not_the_tap_gate(gpu):
+    """PTB_MODE_FAST (opt-in, non-parity): the shading stage's FMA-contracted / approximate-division build.  Trees, rays and hit ids are
+    untouched; the converged-image gate still holds; BSDF taps move by more than the 1e-5 the parity mode keeps -- which is why it is
+    not the default."""
+    gpu.set_mode('fast')
+    try:
+        assert gpu.mode == _native.MODE_FAST
+        g, img, _ = _render_like_golden(gpu, 'cornell_monkey')
+        rmse = rel_rmse(img, g['rgb'])
+        prim_fast = gpu.trace_primary(66)
+        bs = np.load(os.path.join(G, 'bsdf.npz'))
+        geom = np.concatenate([bs['normal'], bs['sign'][:, None], bs['wi'], bs['wo']], 1).astype(np.float32)
+        ev_fast = gpu.eval_bsdf(bs['params'], geom)
+    finally:
+        gpu.set_mode('parity')
+    assert gpu.mode == _native.MODE_PARITY
+    prim = gpu.trace_primary(66)
+    assert np.array_equal(prim['index'], prim_fast['index']) and np.array_equal(bits(prim['depth']), bits(prim_fast['depth']))
+    ev = gpu.eval_bsdf(bs['params'], geom)
+    ok = ~np.isnan(ev).any(1)
+    tap = float((np.abs(ev_fast[ok] - ev[ok]) / np.maximum(np.abs(ev[ok]).max(1, keepdims=True), 1e-4)).max())
+    print(f'fast mode: 1024-spp rel-RMSE {rmse:.3e}; BSDF eval vs parity mode: max rel {tap:.2e}')
+    assert rmse <= 1e-3, rmse
+    assert tap < 5e-3
+
+
 def test_config3_full_resolution(gpu):
     g, img, _ = _render_like_golden(gpu, 'matball')
     ref = g['rgb']

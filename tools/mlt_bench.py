@@ -1,7 +1,9 @@
 """Config 5 (BASELINE.json configs[4], exams/metropolis.py): MLTPathEngine defaults -- 2^18 chains x 32 dimensions per render(),
 LSP 0.25, sigma 0.01 -- on the config-2 scene at 512x512.  Prints device-timed chain proposals/s and Mrays/s.  Run under gpurun."""
 import json
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ptina_b200 import _native, scenes, worker
 from ptina_b200.engine import MLTPathEngine
