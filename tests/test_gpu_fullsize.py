@@ -219,3 +219,71 @@ def test_unmodified_benchmark_script(gpu, tmp_path, capsys, monkeypatch):
     assert np.array_equal(bits(worker.get_image()), bits(img))
     for mod in [k for k in list(__import__('sys').modules) if k == 'ptina' or k.startswith('ptina.') or k == 'taichi']:
         del __import__('sys').modules[mod]
+
+
+def test_unmodified_benchtiles_script(gpu, tmp_path, capsys, monkeypatch):
+    """exams/benchtiles.py, unmodified: render_tile(0, 0, 0) as a warm-up, then render_final(32) -- 8x8 tiles of 64x64 pixels, samples
+    m = 0..32 each (`m > samples: continue` is inclusive) -- against the oracle's restatement of the same loops."""
+    from ptina_b200 import compat
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'benchtiles.py'
+    script.write_text(open(os.path.join(G, 'exams', 'benchtiles.py.txt')).read())
+    os.symlink(os.path.join(root, 'assets'), tmp_path / 'assets')
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(compat.PATH)
+    gpu.sobol_reset()
+    ns = compat.run_script(str(script))
+    assert capsys.readouterr().out.strip().endswith('sps')
+    img = ns['img']
+    film = gpu.get_film(0)
+    assert img.shape == (512, 512, 4) and (film[..., 3] == 33).all() and gpu.sobol_time == 64 + 1 + 64
+    # the oracle on one tile of the same frame (tile (3, 2) is the 3*8 + 2 + 1 = 27th render_tile call after the warm-up one)
+    from ptina_b200.tools.readgltf import readgltf
+    v, m, mats, imgs = readgltf(os.path.join(root, 'assets', 'monkey_cornell.gltf'))
+    o = oracle.Oracle()
+    o.load_materials(mats); o.load_images(imgs); o.load_model(v, m); o.build_tree()
+    o.set_camera(scenes.BENCHMARK_PERS); o.set_size(512, 512)
+    o.sobol_time = 64 + 1 + 3 * 8 + 2
+    o.render_tile(oracle.ENGINE_PATH, 3, 2, 32)
+    a, b = film[192:256, 128:192, :3] / 33, o.get_film(0)[192:256, 128:192, :3] / 33
+    rel = np.abs(a - b).max(2) / np.maximum(np.abs(b).max(2), 1e-2)
+    assert np.median(rel) < 1e-6 and rel_rmse(a, b) < 1e-3, (float(np.median(rel)), rel_rmse(a, b))
+    for mod in [k for k in list(__import__('sys').modules) if k == 'ptina' or k.startswith('ptina.') or k == 'taichi']:
+        del __import__('sys').modules[mod]
+
+
+def test_input_validation(gpu):
+    """Ids that would index past the material / texture tables are refused at load time (host arrays) or at build time (device
+    arrays); taps refuse missing buffers; mlt_state refuses a chain count that is not the context's."""
+    import torch
+    from ptina_b200.model import ModelPool
+    from ptina_b200.tree import BVHTree
+    sc = scenes.cornell_boxes(nx=32, ny=32)
+    scenes.apply(worker, sc)
+    bad = np.array(sc['mtlids'], np.int32); bad[3] = 64
+    with pytest.raises(_native.NativeError, match='material id 64'):
+        ModelPool().load(sc['vertices'], bad)
+    bad[3] = -2
+    with pytest.raises(_native.NativeError, match='material id -2'):
+        ModelPool().load(sc['vertices'], bad)
+    dv = torch.from_numpy(np.ascontiguousarray(sc['vertices'], np.float32)).cuda()
+    ModelPool().load(dv, torch.from_numpy(bad).cuda())
+    with pytest.raises(RuntimeError, match='material ids outside'):
+        BVHTree().build()
+    with pytest.raises(AssertionError, match='float32'):
+        ModelPool().load(dv.double(), torch.from_numpy(bad).cuda())
+    with pytest.raises(_native.NativeError, match='texture id'):
+        worker.set_world_light([1, 1, 1, 1], 64)
+    with pytest.raises(_native.NativeError, match='texture id'):
+        worker.load_materials([scenes.material(tex={'basecolor': 99})])
+    scenes.apply(worker, sc)
+    rays = np.zeros((4, 6), np.float32); rays[:, 5] = 1
+    import ctypes
+    assert gpu.L.ptb_occluded(gpu.h, rays.ctypes.data_as(ctypes.c_void_p), None, None, 4, 0, None) != 0
+    assert b'needs rays, dis and occluded' in gpu.L.ptb_last_error()
+    gpu.mlt_reset(0, 0, 1024)
+    with pytest.raises(_native.NativeError, match='sized for 16 chains'):
+        gpu.mlt_state(16)
+    with pytest.raises(_native.NativeError, match='GL'):
+        gpu.fast_export_gl(1)                 # no OpenGL context on this thread: a clean error, not a crash
+    worker.clear()
