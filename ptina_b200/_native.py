@@ -43,7 +43,7 @@ class Counters(ctypes.Structure):
 
 # every symbol include/ptina_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_set_mode', 'ptb_get_mode', 'ptb_synchronize', 'ptb_flush',
+    'ptb_last_error', 'ptb_version', 'ptb_create', 'ptb_destroy', 'ptb_set_stream', 'ptb_set_mode', 'ptb_get_mode', 'ptb_set_option', 'ptb_synchronize', 'ptb_flush',
     'ptb_set_sobol_table', 'ptb_sobol_reset', 'ptb_sobol_get_time', 'ptb_sobol_set_time', 'ptb_sobol_point',
     'ptb_load_model', 'ptb_load_materials', 'ptb_load_images', 'ptb_clear_lights', 'ptb_add_light', 'ptb_set_world_light',
     'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_export_traversal', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
@@ -160,6 +160,10 @@ class Context:
         """MODE_PARITY (default) or MODE_FAST / 'fast': the shading stage's FMA-contracted, approximate-division build (non-parity)."""
         mode = {'parity': MODE_PARITY, 'fast': MODE_FAST}.get(mode, mode)
         self._check(self.L.ptb_set_mode(self.h, int(mode)))
+
+    def set_option(self, name, value):
+        """Scheduling / builder switches that do not change results (see include/ptina_b200.h ptb_set_option)."""
+        self._check(self.L.ptb_set_option(self.h, name.encode(), int(value)))
 
     @property
     def mode(self):

@@ -92,7 +92,7 @@ static int flush_pending(ptb_ctx* c) {
 // frees everything a context owns (also the partly built context of a failed ptb_create)
 static void release_ctx(ptb_ctx* c) {
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_cache, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
-                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_nodes2, c->d_pl_id[0], c->d_pl_id[1], c->d_pl_depth[0], c->d_pl_depth[1], c->d_pl_nn, c->d_pl_lo[0], c->d_pl_lo[1], c->d_pl_hi[0], c->d_pl_hi[1], c->d_qnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_nodes2, c->d_pl_id[0], c->d_pl_id[1], c->d_pl_depth[0], c->d_pl_depth[1], c->d_pl_nn, c->d_pl_lo[0], c->d_pl_lo[1], c->d_pl_hi[0], c->d_pl_hi[1], c->d_pl_keep, c->d_pl_make, c->d_pl_kpos, c->d_pl_mpos, c->d_pl_S, c->d_qnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
                     c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->tq.e[0], c->tq.e[1], c->tq.e[2], c->tq.e[3], c->tq.e[4], c->tq2.e[0], c->tq2.e[1], c->tq2.e[2], c->tq2.e[3], c->tq2.e[4],
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold, c->d_resolve, c->d_flags};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -101,7 +101,7 @@ static void release_ctx(ptb_ctx* c) {
     if (c->ev_shade) cudaEventDestroy(c->ev_shade);
     if (c->ev_shadow) cudaEventDestroy(c->ev_shadow);
     if (c->stream2) cudaStreamDestroy(c->stream2);
-    for (cudaEvent_t e : {c->ev_shade1, c->ev_shadow1, c->ev_fork, c->ev_join}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_shade1, c->ev_shadow1, c->ev_fork, c->ev_join, c->ev_acc[0], c->ev_acc[1]}) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {c->stream3, c->stream4}) if (st) cudaStreamDestroy(st);
     delete c;
 }
@@ -185,6 +185,19 @@ int ptb_set_mode(ptb_ctx* c, int mode) {
     CHECK_FLUSH(c);
     if (mode != PTB_MODE_PARITY && mode != PTB_MODE_FAST) { ptb_set_error("unknown mode %d", mode); return 1; }
     if (c->fast_shade != (mode == PTB_MODE_FAST)) { c->fast_shade = mode == PTB_MODE_FAST; c->params_dirty = true; }   // the per-scene cache is recomputed by the build in use
+    return 0;
+}
+int ptb_set_option(ptb_ctx* c, const char* name, int value) {
+    CHECK_FLUSH(c);
+    const std::string k = name ? name : "";
+    if (k == "coalesce") c->coalesce = value != 0;
+    else if (k == "overlap_shadow") c->overlap_shadow = value != 0;
+    else if (k == "pt_two_lanes") c->pt_two_lanes = value != 0;
+    else if (k == "mlt_two_lanes") c->mlt_two_lanes = value != 0;
+    else if (k == "use_ploc") c->use_ploc = value != 0;
+    else if (k == "ploc_big") c->ploc_big = value != 0;
+    else if (k == "ploc_radius") { if (value < 1 || value > 1024) { ptb_set_error("ploc_radius outside [1, 1024]"); return 1; } c->ploc_radius = value; }
+    else { ptb_set_error("unknown option '%s'", k.c_str()); return 1; }
     return 0;
 }
 int ptb_get_mode(ptb_ctx* c, int* mode) { CHECK_CTX(c); *mode = c->fast_shade ? PTB_MODE_FAST : PTB_MODE_PARITY; return 0; }

@@ -492,6 +492,96 @@ __global__ void __launch_bounds__(1024) k_ploc_small(const float4* __restrict__ 
     if (tid == 0) scal[15] = B.depth[cur][0];
 }
 
+// ---- the same clustering for trees of any size, one kernel per step of a round (round 2) --------------------------------------------------
+// Scenes beyond PTB_SMALL_TREE kept the LBVH topology in round 1.  The build of a 1 M-triangle scene is amortised over a render of
+// seconds, so the traversal tree is now rebuilt by PLOC at every size: k_plocb_init compacts the unlisted, testable leaf slots into the
+// cluster arrays (positions from a device-wide exclusive scan); every round runs k_plocb_nn (nearest neighbour by union surface area
+// within +-radius along the current order), k_plocb_flags (who survives / which pairs merge; mutual nearest neighbours merge, the lower
+// index keeps the slot), two scans, and k_plocb_merge (writes the merged clusters and their Node64).  Deterministic: ties go to the
+// lower index, node numbers are assigned by the scan.  Node (m0 - 2) - k is the k-th node created, so the root is node 0.
+// Device scalars (ints): S[0] = clusters in the current round, S[1] = nodes created so far, S[2] = m0, S[3] = height of the last cluster.
+__global__ void __launch_bounds__(BLK) k_plocb_flags0(const float4* __restrict__ tlo, int n, int* __restrict__ flag) {
+    int s = blockIdx.x * BLK + threadIdx.x;
+    if (s < n) flag[s] = (__float_as_int(tlo[s].w) & (PTB_TF_NEVER | PTB_TF_LISTED)) == 0;
+}
+__global__ void __launch_bounds__(BLK) k_plocb_init(const float4* __restrict__ tlo, const float4* __restrict__ thi, const float4* __restrict__ gbox, int n,
+                                                    const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ id, float4* __restrict__ lo, float4* __restrict__ hi,
+                                                    int* __restrict__ depth, int* __restrict__ S) {
+    int s = blockIdx.x * BLK + threadIdx.x;
+    if (s >= n) return;
+    if (s == n - 1) { const int m0 = pos[s] + flag[s]; S[0] = m0; S[1] = 0; S[2] = m0; S[3] = 0; }
+    if (!flag[s]) return;
+    const int fl = __float_as_int(tlo[s].w);
+    const bool must = (fl & PTB_TF_MUST) != 0;          // ill-conditioned: bounded by its gate box, never culled by distance
+    const int k = pos[s];
+    id[k] = must ? (s | PTB_NODE_MUST) : s;
+    lo[k] = must ? gbox[2 * s] : tlo[s];
+    hi[k] = must ? gbox[2 * s + 1] : thi[s];
+    depth[k] = 0;
+}
+__global__ void __launch_bounds__(BLK) k_plocb_nn(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ S, int radius, int* __restrict__ nn) {
+    const int m = S[0];
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    const float4 alo = lo[i], ahi = hi[i];
+    float best = 0.0f; int bj = -1;
+    const int j0 = max(0, i - radius), j1 = min(m - 1, i + radius);
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const float c = ploc_cost(alo, ahi, __ldg(&lo[j]), __ldg(&hi[j]));
+        if (bj < 0 || c < best) { best = c; bj = j; }
+    }
+    nn[i] = bj;
+}
+__global__ void __launch_bounds__(BLK) k_plocb_flags(const int* __restrict__ nn, const int* __restrict__ S, int* __restrict__ keep, int* __restrict__ make) {
+    const int m = S[0];
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == i;
+    keep[i] = !(mutual && j < i);
+    make[i] = mutual && i < j;
+}
+__global__ void __launch_bounds__(BLK) k_plocb_merge(const int* __restrict__ nn, const int* __restrict__ keep, const int* __restrict__ kpos, const int* __restrict__ mpos,
+                                                     const int* __restrict__ id, const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ depth,
+                                                     int* __restrict__ id2, float4* __restrict__ lo2, float4* __restrict__ hi2, int* __restrict__ depth2,
+                                                     int n, const int* __restrict__ S, Node64* __restrict__ nodes) {
+    const int m = S[0], created = S[1], m0 = S[2];
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m || !keep[i]) return;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == i;           // keep[i] && mutual  =>  i < j
+    int cid = id[i], cdep = depth[i];
+    float4 clo = lo[i], chi = hi[i];
+    if (mutual) {
+        const int node = (m0 - 2) - (created + mpos[i]);
+        const float4 blo = lo[j], bhi = hi[j];
+        const int idj = id[j];
+        Node64 N;
+        N.a = make_float4(clo.x, clo.y, clo.z, __int_as_float(cid));
+        N.b = make_float4(chi.x, chi.y, chi.z, __int_as_float(idj));
+        N.c = make_float4(blo.x, blo.y, blo.z, 0.0f);
+        N.d = make_float4(bhi.x, bhi.y, bhi.z, 0.0f);
+        nodes[node] = N;
+        clo = make_float4(fminf(clo.x, blo.x), fminf(clo.y, blo.y), fminf(clo.z, blo.z), 0.0f);
+        chi = make_float4(fmaxf(chi.x, bhi.x), fmaxf(chi.y, bhi.y), fmaxf(chi.z, bhi.z), 0.0f);
+        cid = (n + node) | ((cid | idj) & PTB_NODE_MUST);
+        cdep = max(cdep, depth[j]) + 1;
+    }
+    const int k = kpos[i];
+    id2[k] = cid; lo2[k] = clo; hi2[k] = chi; depth2[k] = cdep;
+}
+// after the merge of a round: new cluster count, nodes created so far, height of the (eventually only) cluster 0
+__global__ void k_plocb_next(const int* __restrict__ keep, const int* __restrict__ make, const int* __restrict__ kpos, const int* __restrict__ mpos,
+                             const int* __restrict__ depth2, int* S, int* __restrict__ scal) {
+    const int m = S[0];
+    const int m2 = kpos[m - 1] + keep[m - 1];
+    S[1] += mpos[m - 1] + make[m - 1];
+    S[0] = m2;
+    S[3] = depth2[0];
+    if (m2 == 1) scal[15] = depth2[0];
+}
+
 // Node32 (ptb_traverse.cuh): the boxes of a packed node on the 15-bit grid, rounded outward.  The candidate from the f32 estimate is
 // corrected against the exact value of the plane it decodes to (base + (1 + q/32768) * ext: a 24-bit plus a 16-bit number of
 // nearby exponents, exact in double), so lo' <= lo and hi' >= hi hold as real numbers whatever the rounding of the estimate.
@@ -557,6 +647,59 @@ __global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ ver
 inline int nblk(int n) { return (n + BLK - 1) / BLK; }
 
 }  // namespace
+
+// PLOC over a tree of any size (kernels k_plocb_*).  The round loop reads the cluster count back once per round: the build of a big
+// scene is paid once per render, not per frame.  Leaves scal[15] = height of the tree, or -1 if it did not converge (LBVH topology stays).
+static int ptb_ploc_big(ptb_ctx* c, int n) {
+    cudaStream_t st = c->stream;
+    if (c->pl_cap < n) {      // grow-only cluster buffers and the second node array
+        void** bufs[] = {(void**)&c->d_pl_id[0], (void**)&c->d_pl_id[1], (void**)&c->d_pl_depth[0], (void**)&c->d_pl_depth[1], (void**)&c->d_pl_nn, (void**)&c->d_pl_keep, (void**)&c->d_pl_make,
+                         (void**)&c->d_pl_kpos, (void**)&c->d_pl_mpos, (void**)&c->d_pl_lo[0], (void**)&c->d_pl_lo[1], (void**)&c->d_pl_hi[0], (void**)&c->d_pl_hi[1], (void**)&c->d_nodes2};
+        const size_t elem[] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 16, 16, 16, 16, sizeof(Node64)};
+        PTB_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 14; k++) { cudaFree(*bufs[k]); *bufs[k] = nullptr; PTB_CUDA(cudaMalloc(bufs[k], elem[k] * (size_t)(n + 8))); }
+        c->pl_cap = n;
+    }
+    if (!c->d_pl_S) PTB_CUDA(cudaMalloc((void**)&c->d_pl_S, 16));
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, c->d_pl_keep, c->d_pl_kpos, n, st);
+    if (need > c->sort_tmp_bytes) {
+        PTB_CUDA(cudaStreamSynchronize(st));
+        if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
+        PTB_CUDA(cudaMalloc(&c->d_sort_tmp, need));
+        c->sort_tmp_bytes = need;
+    }
+    size_t tmp = c->sort_tmp_bytes;
+    PTB_CUDA(cudaMemsetAsync(c->d_nodes2, 0xFF, sizeof(Node64) * (size_t)(n - 1), st));      // ids -1: slots the PLOC tree leaves unused
+    k_plocb_flags0<<<nblk(n), BLK, 0, st>>>(c->d_tlo, n, c->d_pl_keep);
+    PTB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp, tmp, c->d_pl_keep, c->d_pl_kpos, n, st));
+    k_plocb_init<<<nblk(n), BLK, 0, st>>>(c->d_tlo, c->d_thi, c->d_gbox, n, c->d_pl_keep, c->d_pl_kpos, c->d_pl_id[0], c->d_pl_lo[0], c->d_pl_hi[0], c->d_pl_depth[0], c->d_pl_S);
+    c->launches += 3;
+    int hS[4] = {0, 0, 0, 0};
+    PTB_CUDA(cudaMemcpyAsync(hS, c->d_pl_S, sizeof hS, cudaMemcpyDeviceToHost, st));
+    PTB_CUDA(cudaStreamSynchronize(st));
+    int m = hS[0], cur = 0, rounds = 0;
+    if (m < 2) return 0;                                   // scal[15] stays -1: nothing to cluster
+    for (; m > 1 && rounds < 256; rounds++) {
+        k_plocb_nn<<<nblk(m), BLK, 0, st>>>(c->d_pl_lo[cur], c->d_pl_hi[cur], c->d_pl_S, c->ploc_radius, c->d_pl_nn);
+        k_plocb_flags<<<nblk(m), BLK, 0, st>>>(c->d_pl_nn, c->d_pl_S, c->d_pl_keep, c->d_pl_make);
+        tmp = c->sort_tmp_bytes;
+        PTB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp, tmp, c->d_pl_keep, c->d_pl_kpos, m, st));
+        tmp = c->sort_tmp_bytes;
+        PTB_CUDA(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp, tmp, c->d_pl_make, c->d_pl_mpos, m, st));
+        k_plocb_merge<<<nblk(m), BLK, 0, st>>>(c->d_pl_nn, c->d_pl_keep, c->d_pl_kpos, c->d_pl_mpos, c->d_pl_id[cur], c->d_pl_lo[cur], c->d_pl_hi[cur], c->d_pl_depth[cur],
+                                               c->d_pl_id[cur ^ 1], c->d_pl_lo[cur ^ 1], c->d_pl_hi[cur ^ 1], c->d_pl_depth[cur ^ 1], n, c->d_pl_S, c->d_nodes2);
+        k_plocb_next<<<1, 1, 0, st>>>(c->d_pl_keep, c->d_pl_make, c->d_pl_kpos, c->d_pl_mpos, c->d_pl_depth[cur ^ 1], c->d_pl_S, c->d_scalars);
+        c->launches += 6;
+        PTB_CUDA(cudaMemcpyAsync(hS, c->d_pl_S, sizeof hS, cudaMemcpyDeviceToHost, st));
+        PTB_CUDA(cudaStreamSynchronize(st));
+        if (hS[0] >= m) break;                             // no pair merged: cannot happen (the global minimum is mutual), guards the loop
+        m = hS[0];
+        cur ^= 1;
+    }
+    c->ploc_rounds = rounds;
+    return 0;
+}
 
 int ptb_lbvh_build(ptb_ctx* c) {
     const int n = c->nfaces;
@@ -631,6 +774,9 @@ int ptb_lbvh_build(ptb_ctx* c) {
         else for (int lvl = 1; lvl <= sweeps; lvl++) k_tbox_level<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_ready, n, lvl, c->d_bmin, c->d_bmax, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi);
         k_pack_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_child, c->d_bmin, c->d_bmax, n, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_nodes, c->d_gate, c->d_gbox);
         c->launches += small ? 5 : 4 + sweeps;
+        if (!small && c->use_ploc && c->ploc_big) {
+            if (ptb_ploc_big(c, n)) return 1;
+        }
         if (small && c->use_ploc) {
             PlocBufs B;
             for (int k = 0; k < 2; k++) { B.id[k] = c->d_pl_id[k]; B.lo[k] = c->d_pl_lo[k]; B.hi[k] = c->d_pl_hi[k]; B.depth[k] = c->d_pl_depth[k]; }
@@ -672,7 +818,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
         c->list_n = n > 1 ? h_scal[11] : 0;
         for (int k = 0; k < 3; k++) { c->root_lo[k] = h_root[k]; c->root_hi[k] = h_root[3 + k]; }
         // the PLOC tree replaces the LBVH topology for traversal when it was built and fits the traversal stack
-        c->trav_depth = (n > 1 && n - 1 <= PTB_SMALL_TREE && c->use_ploc) ? h_scal[15] : -1;
+        c->trav_depth = (n > 1 && c->use_ploc && (n - 1 <= PTB_SMALL_TREE || c->ploc_big)) ? h_scal[15] : -1;
         c->d_nodes_active = (c->trav_depth >= 1 && c->trav_depth <= PTB_STACK) ? c->d_nodes2 : c->d_nodes;
         // quantised nodes for a tree too big to be resident as 64-byte nodes (wavefront.cu launch_trace_io decides the same way)
         if (valid && ptb_tree_mode(c, n) != PTB_TREE_RESIDENT) {

@@ -56,15 +56,15 @@ struct DevCounters {
 
 // A frame covers the whole film, or -- render_tile (engine/path.py:96-118) -- one 64x64 window of it at (x0, y0); in window mode
 // every sample m of a pixel uses the SAME Sobol point with its own dimension rotation wanghash3(x, y, m) (path.py:115).
-struct FrameMap { int nx, ny, tiles_y, pps, x0, y0, window; };   // pps = path slots per sample (multiple of 32)
+struct FrameMap { int nx, ny, tiles_y, pps, x0, y0, window, slot_base; };   // pps = path slots per sample (multiple of 32); slot_base: first path slot of the lane
 __host__ __device__ inline FrameMap make_frame(int nx, int ny) {
-    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = 0; f.y0 = 0; f.window = 0;
+    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = 0; f.y0 = 0; f.window = 0; f.slot_base = 0;
     int tx = (nx + 7) / 8; f.tiles_y = (ny + 3) / 4;
     f.pps = tx * f.tiles_y * 32;
     return f;
 }
 __host__ __device__ inline FrameMap make_window(int nx, int ny, int x0, int y0, int w, int h) {
-    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = x0; f.y0 = y0; f.window = 1;
+    FrameMap f; f.nx = nx; f.ny = ny; f.x0 = x0; f.y0 = y0; f.window = 1; f.slot_base = 0;
     int tx = (w + 7) / 8; f.tiles_y = (h + 3) / 4;
     f.pps = tx * f.tiles_y * 32;
     return f;
@@ -122,6 +122,11 @@ struct ptb_ctx {
     Node64* d_nodes2 = nullptr;     // PLOC traversal tree of small scenes (lbvh.cu k_ploc_small); d_nodes_active = the one traversed
     Node64* d_nodes_active = nullptr;
     int *d_pl_id[2]{}, *d_pl_depth[2]{}, *d_pl_nn = nullptr; float4 *d_pl_lo[2]{}, *d_pl_hi[2]{};   // PLOC cluster buffers
+    int *d_pl_keep = nullptr, *d_pl_make = nullptr, *d_pl_kpos = nullptr, *d_pl_mpos = nullptr, *d_pl_S = nullptr;   // multi-block PLOC (big trees)
+    int pl_cap = 8200;              // entries the PLOC buffers and d_nodes2 hold
+    bool ploc_big = true;           // PTB_NO_PLOC_BIG=1: trees beyond 8193 triangles keep the LBVH topology for traversal
+    int ploc_radius = 16;           // PTB_PLOC_RADIUS: search radius of the multi-block PLOC
+    int ploc_rounds = 0;
     bool use_ploc = true;           // PTB_NO_PLOC=1: keep the LBVH topology for traversal
     int trav_depth = -1;
     uint4* d_qnodes = nullptr;      // [2(n-1)] quantised copy of d_nodes (Node32), built for trees that are traversed out of global memory
@@ -159,6 +164,8 @@ struct ptb_ctx {
     cudaStream_t stream3 = nullptr, stream4 = nullptr;            // lane 1: main and side stream
     cudaEvent_t ev_shade1 = nullptr, ev_shadow1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     bool mlt_two_lanes = true;      // PTB_MLT_ONE_LANE=1: the whole chain population as one wavefront
+    bool pt_two_lanes = true;       // PTB_PT_ONE_LANE=1: multi-batch renders run their batches one after the other
+    cudaEvent_t ev_acc[2]{};        // accumulate of the last chunk of each lane (chunks add to the film in Sobol order)
     bool overlap_shadow = true;     // PTB_NO_OVERLAP=1 turns the overlap off
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* 
             Rng rng;
             if (dim == 0) { rng.tab = rngtab + (size_t)p * rng_stride; rng.base = 0; rng.dim = 0; }
             else {
-                int s = p / fm.pps, q = p - s * fm.pps, x, y;
+                const int lp = p - fm.slot_base;                      // slot within the lane's share of the pool
+                int s = lp / fm.pps, q = lp - s * fm.pps, x, y;
                 slot_pixel(fm, q, &x, &y);
                 frame_rng(fm, rngtab, dim, s, x, y, &rng);
             }

@@ -68,16 +68,17 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
                 float fx = ((float)x + dx) / (float)fm.nx * 2.0f - 1.0f;
                 float fy = ((float)y + dy) / (float)fm.ny * 2.0f - 1.0f;
                 camera_generate(P, fx, fy, &ro, &rd);
-                st.ray_o[p] = make_float4(ro.x, ro.y, ro.z, 0.0f);
-                st.ray_d[p] = make_float4(rd.x, rd.y, rd.z, 0.0f);
-                st.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));              // depth = 0
-                st.result[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                         // last_brdf_pdf = 0
+                const int slot = fm.slot_base + p;
+                st.ray_o[slot] = make_float4(ro.x, ro.y, ro.z, 0.0f);
+                st.ray_d[slot] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+                st.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(0));           // depth = 0
+                st.result[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);                      // last_brdf_pdf = 0
             }
         }
         int pos = block_append<BLK>(live, &ctrl->n_in, s_warp, &s_base);
         if (live) {
             if (renorm) rd = normalized(rd);
-            xq.o[pos] = make_float4(ro.x, ro.y, ro.z, __int_as_float(p));
+            xq.o[pos] = make_float4(ro.x, ro.y, ro.z, __int_as_float(fm.slot_base + p));
             xq.d[pos] = make_float4(rd.x, rd.y, rd.z, __int_as_float(-1));                 // avoid = -1
         }
     }
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(BLK) k_preview(const SceneParams* __restrict__
     size_t pix = (size_t)x * fm.ny + y;
     float4 a = film1[pix], b = film2[pix];
     for (int s = 0; s < nsamp; s++) {
-        int p = s * fm.pps + q;
+        int p = fm.slot_base + s * fm.pps + q;
         float4 o4 = st.ray_o[p], d4 = st.ray_d[p], h4 = st.hit[p];
         V3 albedo = v3s(0.0f), normal = v3s(0.0f);
         int hit_index = __float_as_int(h4.w);
@@ -117,13 +118,13 @@ __global__ void __launch_bounds__(BLK) k_accumulate(float4* __restrict__ film, c
     if (!slot_pixel(fm, q, &x, &y)) return;
     size_t pix = (size_t)x * fm.ny + y;
     if (sample_out) {   // tap: radiance of the first sample, film untouched
-        float4 r = result[q];
+        float4 r = result[fm.slot_base + q];
         sample_out[3 * pix] = r.x; sample_out[3 * pix + 1] = r.y; sample_out[3 * pix + 2] = r.z;
         return;
     }
     float4 f = film[pix];
     for (int s = 0; s < nsamp; s++) {
-        float4 r = result[(size_t)s * fm.pps + q];
+        float4 r = result[fm.slot_base + (size_t)s * fm.pps + q];
         f = make_float4(f.x + r.x, f.y + r.y, f.z + r.z, f.w + 1.0f);
     }
     film[pix] = f;
@@ -168,10 +169,10 @@ __global__ void __launch_bounds__(BLK) k_gather_primary(FrameMap fm, PathState s
     if (!slot_pixel(fm, q, &x, &y)) return;
     size_t pix = (size_t)x * fm.ny + y;
     if (which == 0) {
-        float4 o = st.ray_o[q], d = st.ray_d[q];
+        float4 o = st.ray_o[fm.slot_base + q], d = st.ray_d[fm.slot_base + q];
         rays[6 * pix] = o.x; rays[6 * pix + 1] = o.y; rays[6 * pix + 2] = o.z; rays[6 * pix + 3] = d.x; rays[6 * pix + 4] = d.y; rays[6 * pix + 5] = d.z;
     } else {
-        float4 h = st.hit[q];
+        float4 h = st.hit[fm.slot_base + q];
         int id = __float_as_int(h.w);
         if (hit) hit[pix] = id >= 0;
         if (depth) depth[pix] = h.x;
@@ -429,6 +430,8 @@ int ptb_wf_init(ptb_ctx* c) {
     c->quant_resident_bvh = getenv("PTB_QUANT_RESIDENT_BVH") != nullptr;
     c->overlap_shadow = getenv("PTB_NO_OVERLAP") == nullptr;
     c->use_ploc = getenv("PTB_NO_PLOC") == nullptr;
+    c->ploc_big = getenv("PTB_NO_PLOC_BIG") == nullptr;
+    if (const char* r = getenv("PTB_PLOC_RADIUS")) { const int v = atoi(r); if (v >= 1 && v <= 1024) c->ploc_radius = v; }
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shadow, cudaEventDisableTiming));
@@ -436,6 +439,8 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&c->ev_shade1, &c->ev_shadow1, &c->ev_fork, &c->ev_join}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     c->mlt_two_lanes = getenv("PTB_MLT_ONE_LANE") == nullptr;
+    c->pt_two_lanes = getenv("PTB_PT_ONE_LANE") == nullptr;
+    for (cudaEvent_t* e : {&c->ev_acc[0], &c->ev_acc[1]}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
@@ -521,6 +526,7 @@ static int run_bounces(ptb_ctx* c, const Lane& L, const float* rngtab, int dim, 
 int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, float* sample_out_dev, const int* window) {
     if (c->nx <= 0 || c->ny <= 0) { ptb_set_error("film size not set (ptb_set_size)"); return 1; }
     if (c->tree_n != c->nfaces) { ptb_set_error("BVH is stale: call ptb_build_tree after ptb_load_model"); return 1; }
+    if (engine != PTB_ENGINE_MLT && !c->d_sobolV) { ptb_set_error("Sobol direction table not set (ptb_set_sobol_table)"); return 1; }
     if (ptb_wf_upload_params(c)) return 1;
     cudaStream_t st = c->stream;
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
@@ -563,36 +569,53 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
     if (window && count > per_batch) { ptb_set_error("a window of %d samples needs %lld path slots, pool has %lld", count, (long long)count * fm.pps, (long long)c->max_paths); return 1; }
     if (per_batch < 1) { ptb_set_error("film %dx%d needs %d path slots per sample, pool has %lld", c->nx, c->ny, fm.pps, (long long)c->max_paths); return 1; }
     if (sample_out_dev) count = 1;
-    for (int done = 0; done < count; done += per_batch) {
-        int ns = count - done < per_batch ? count - done : per_batch;
-        if (ensure_sobolP(c, ns)) return 1;
+    // A render of several batches (config 4: 4 samples of a 1080p film fill the pool) runs its batches as half-sized chunks that
+    // alternate between the two lanes: chunk b+1 traces while chunk b drains, each filling the SMs the other's persistent kernels leave
+    // idle.  Chunks add to the film in Sobol order (the accumulate of chunk b waits for that of chunk b-1), so the film is bit-identical.
+    const int half = (int)((c->max_paths / 2) / fm.pps);
+    const bool two = c->pt_two_lanes && !c->profiling && !window && !sample_out_dev && engine != PTB_ENGINE_PREVIEW && count > per_batch && half >= 1;
+    const int chunk = two ? half : per_batch;
+    if (ensure_sobolP(c, two ? 2 * chunk : (count < chunk ? count : chunk))) return 1;
+    if (two) { PTB_CUDA(cudaEventRecord(c->ev_fork, st)); PTB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0)); }
+    int b = 0;
+    for (int done = 0; done < count; done += chunk, b++) {
+        const int ns = count - done < chunk ? count - done : chunk;
+        const int w = two ? (b & 1) : 0;
+        const Lane L = ptb_lane(c, w);
+        cudaStream_t ls = L.s_main;
+        FrameMap lfm = fm;
+        lfm.slot_base = w ? (int)(c->max_paths / 2) : 0;
+        float* P = c->d_sobolP + (size_t)w * chunk * c->sobol_dim;
         ptb_stage_begin(c, ST_RAYGEN);
-        if (window ? ptb_wf_sobol_points(c, k_first, 1, 1, c->d_sobolP) : ptb_wf_sobol_points(c, k_first + done * stride, ns, stride, c->d_sobolP)) return 1;
-        k_ctrl_begin<<<1, 1, 0, st>>>(L0.ctrl, 0);
-        k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, ns, engine != PTB_ENGINE_PREVIEW, c->st, L0.xq[0], L0.ctrl, ctr);
+        k_sobol_points<<<nblk(c->sobol_dim, 256), 256, 0, ls>>>(c->d_sobolV, c->sobol_dim, window ? k_first : k_first + done * stride, window ? 1 : ns, window ? 1 : stride, P);
+        k_ctrl_begin<<<1, 1, 0, ls>>>(L.ctrl, 0);
+        k_raygen<<<c->blocks_generic, BLK, 0, ls>>>(c->d_params, P, c->sobol_dim, lfm, ns, engine != PTB_ENGINE_PREVIEW, c->st, L.xq[0], L.ctrl, ctr);
         ptb_stage_end(c);
-        c->launches += 2;
+        c->launches += 3;
         if (engine == PTB_ENGINE_PREVIEW) {
             TraceScene S = ptb_trace_scene(c);
             int policy = ptb_effective_policy(c, c->traversal_request);
             ptb_stage_begin(c, ST_EXTEND);
-            launch_extend(c, L0, S, policy, L0.xq[0]);
+            launch_extend(c, L, S, policy, L.xq[0]);
             ptb_stage_end(c);
             ptb_stage_begin(c, ST_ACCUM);
             size_t pass = (size_t)c->caps.max_filmsize;
-            k_preview<<<nblk(fm.pps), BLK, 0, st>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, fm, ns, c->st, c->d_film + pass, c->d_film + 2 * pass);
+            k_preview<<<nblk(fm.pps), BLK, 0, ls>>>(c->d_params, c->d_texels, c->d_verts, c->d_mtlids, lfm, ns, c->st, c->d_film + pass, c->d_film + 2 * pass);
             ptb_stage_end(c);
             c->launches += 1;
             continue;
         }
-        int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, L0, c->d_sobolP, c->sobol_dim, 0, fm)
-                                           : run_bounces<PTB_ENGINE_BRUTE>(c, L0, c->d_sobolP, c->sobol_dim, 0, fm);
+        int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, L, P, c->sobol_dim, 0, lfm)
+                                           : run_bounces<PTB_ENGINE_BRUTE>(c, L, P, c->sobol_dim, 0, lfm);
         if (rc) return 1;
+        if (two && b > 0) PTB_CUDA(cudaStreamWaitEvent(ls, c->ev_acc[w ^ 1], 0));       // Sobol order of the additions into the film
         ptb_stage_begin(c, ST_ACCUM);
-        k_accumulate<<<nblk(fm.pps), BLK, 0, st>>>(c->d_film, c->st.result, fm, ns, sample_out_dev);
+        k_accumulate<<<nblk(fm.pps), BLK, 0, ls>>>(c->d_film, c->st.result, lfm, ns, sample_out_dev);
         ptb_stage_end(c);
+        if (two) PTB_CUDA(cudaEventRecord(c->ev_acc[w], ls));
         c->launches++;
     }
+    if (two) { PTB_CUDA(cudaEventRecord(c->ev_join, c->stream3)); PTB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0)); }
     PTB_CUDA(cudaGetLastError());
     return 0;
 }

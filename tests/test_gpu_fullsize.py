@@ -114,6 +114,7 @@ def test_config4_full_size_against_oracle(gpu):
     worker.clear()
     o = oracle.Oracle(); scenes.apply(o, sc)
     assert gpu.tree.n == len(sc['mtlids']) > 1_000_000 and gpu.tree.policy == _native.TRAVERSE_ORDERED
+    assert gpu.tree.trav_ploc == 1 and 0 < gpu.tree.trav_depth <= 64       # the multi-block PLOC tree is what the production policy walks
     ta, tb = gpu.export_tree(), o.export_tree()
     for key in ('mc', 'id', 'leaf', 'child'):
         assert np.array_equal(ta[key], tb[key]), key
@@ -150,6 +151,29 @@ def test_config4_full_size_against_oracle(gpu):
     ra, rb = gpu.render_sample(_native.ENGINE_PATH, 66), o.render_sample(oracle.ENGINE_PATH, 66)
     rel = np.abs(ra - rb).max(2) / np.maximum(np.abs(rb).max(2), 1e-2)
     assert np.median(rel) < 1e-6 and (rel > 1e-4).mean() < 0.02, (float(np.median(rel)), float((rel > 1e-4).mean()))
+
+
+def test_two_lane_schedules_are_bit_identical(gpu):
+    """Multi-batch renders alternate half-sized chunks between two lanes, and the big-tree PLOC rebuild changes the traversal tree:
+    neither may change a bit of the film.  1920x1080 fills the path pool with 4 samples, so 10 samples are 5 chunks on 2 lanes."""
+    sc = dict(scenes.mega_small(), size=(1920, 1080))
+    films = {}
+    for key, opts in (('two', {}), ('one', {'pt_two_lanes': 0}), ('lbvh', {'ploc_big': 0})):
+        for k, v in opts.items():
+            gpu.set_option(k, v)
+        try:
+            gpu.sobol_reset()
+            scenes.apply(worker, sc)
+            worker.clear()
+            gpu.render(_native.ENGINE_PATH, 10)
+            films[key] = gpu.get_film().copy()
+            assert gpu.tree.trav_ploc == (0 if key == 'lbvh' else 1)
+        finally:
+            for k in opts:
+                gpu.set_option(k, 1)
+    assert (films['two'][..., 3] == 10).all()
+    assert np.array_equal(bits(films['two']), bits(films['one'])) and np.array_equal(bits(films['two']), bits(films['lbvh']))
+    scenes.apply(worker, sc)       # back to the default tree
 
 
 def test_percall_render_is_coalesced(gpu):

@@ -97,7 +97,7 @@ def test_traversal_structure_is_a_conservative_tree(gpu, name):
     sc, o = load(gpu, name, SMALL[name], ref=False)
     t = gpu.export_traversal()
     n = t['leaf_lo'].shape[0]
-    assert t['ploc'] == (n - 1 <= 8192)
+    assert t['ploc']        # PLOC topology at every size (single-block kernel up to 8193 triangles, the multi-block one beyond)
     nodes = t['nodes']
     ids = np.stack([nodes[:, 3].view(np.int32), nodes[:, 7].view(np.int32)], 1)
     lo = np.stack([nodes[:, 0:3], nodes[:, 8:11]], 1); hi = np.stack([nodes[:, 4:7], nodes[:, 12:15]], 1)
