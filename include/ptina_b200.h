@@ -93,7 +93,7 @@ int ptb_set_stream(ptb_ctx* ctx, void* cuda_stream);
 int ptb_set_mode(ptb_ctx* ctx, int mode);                           /* PTB_MODE_*; PTB_FAST=1 in the environment makes FAST the default */
 int ptb_get_mode(ptb_ctx* ctx, int* mode);
 /* scheduling / builder switches that do NOT change results (tests and measurements flip them at run time; the environment variables of
- * INTEGRATION.md section 3 set their defaults): "coalesce", "overlap_shadow", "pt_two_lanes", "mlt_two_lanes", "use_ploc", "ploc_big",
+ * INTEGRATION.md section 3 set their defaults): "coalesce", "overlap_shadow", "pt_lanes" and "mlt_lanes" (1..4), "use_ploc", "ploc_big",
  * "ploc_radius".  The tree options take effect at the next ptb_build_tree. */
 int ptb_set_option(ptb_ctx* ctx, const char* name, int value);
 int ptb_synchronize(ptb_ctx* ctx);                                  /* worker.py:17-18 */

@@ -101,8 +101,11 @@ static void release_ctx(ptb_ctx* c) {
     if (c->ev_shade) cudaEventDestroy(c->ev_shade);
     if (c->ev_shadow) cudaEventDestroy(c->ev_shadow);
     if (c->stream2) cudaStreamDestroy(c->stream2);
-    for (cudaEvent_t e : {c->ev_shade1, c->ev_shadow1, c->ev_fork, c->ev_join, c->ev_acc[0], c->ev_acc[1]}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t st : {c->stream3, c->stream4}) if (st) cudaStreamDestroy(st);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int w = 0; w < PTB_MAX_LANES; w++) {
+        for (cudaEvent_t e : {c->lane_shade[w], c->lane_shadow[w], c->lane_join[w], c->ev_acc[w]}) if (e) cudaEventDestroy(e);
+        for (cudaStream_t st : {c->lane_main[w], c->lane_side[w]}) if (st) cudaStreamDestroy(st);
+    }
     delete c;
 }
 
@@ -192,8 +195,10 @@ int ptb_set_option(ptb_ctx* c, const char* name, int value) {
     const std::string k = name ? name : "";
     if (k == "coalesce") c->coalesce = value != 0;
     else if (k == "overlap_shadow") c->overlap_shadow = value != 0;
-    else if (k == "pt_two_lanes") c->pt_two_lanes = value != 0;
-    else if (k == "mlt_two_lanes") c->mlt_two_lanes = value != 0;
+    else if (k == "pt_lanes" || k == "mlt_lanes") {
+        if (value < 1 || value > PTB_MAX_LANES) { ptb_set_error("%s outside [1, %d]", k.c_str(), PTB_MAX_LANES); return 1; }
+        (k == "pt_lanes" ? c->pt_lanes : c->mlt_lanes) = value;
+    }
     else if (k == "use_ploc") c->use_ploc = value != 0;
     else if (k == "ploc_big") c->ploc_big = value != 0;
     else if (k == "ploc_radius") { if (value < 1 || value > 1024) { ptb_set_error("ploc_radius outside [1, 1024]"); return 1; } c->ploc_radius = value; }

@@ -73,6 +73,7 @@ __host__ __device__ inline FrameMap make_window(int nx, int ny, int x0, int y0, 
 // A lane = one wavefront in flight: its queues, control block, streams and events.  Lane 0 is the context's own (whole pools, the
 // caller's stream); lane 1 works in the upper half of every pool on streams of its own, so two independent populations of paths
 // (the two halves of the MLT chains) can be on the device at once -- each fills the SMs the other's small kernels leave idle.
+#define PTB_MAX_LANES 4
 struct Ctrl;
 struct Lane {
     RayQueue xq[2]; RayQueue sq; ExpQ tq, tq2;
@@ -161,11 +162,12 @@ struct ptb_ctx {
     ExpQ tq2{};                     // second tree queue: the shadow stage of bounce b runs beside the extend stage of bounce b+1
     cudaStream_t stream2 = nullptr; // non-blocking side stream of the shadow stage
     cudaEvent_t ev_shade = nullptr, ev_shadow = nullptr;
-    cudaStream_t stream3 = nullptr, stream4 = nullptr;            // lane 1: main and side stream
-    cudaEvent_t ev_shade1 = nullptr, ev_shadow1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
-    bool mlt_two_lanes = true;      // PTB_MLT_ONE_LANE=1: the whole chain population as one wavefront
-    bool pt_two_lanes = true;       // PTB_PT_ONE_LANE=1: multi-batch renders run their batches one after the other
-    cudaEvent_t ev_acc[2]{};        // accumulate of the last chunk of each lane (chunks add to the film in Sobol order)
+    // lanes 1..PTB_MAX_LANES-1: main and side stream, shade / shadow events (lane 0 uses stream / stream2 / ev_shade / ev_shadow)
+    cudaStream_t lane_main[PTB_MAX_LANES]{}, lane_side[PTB_MAX_LANES]{};
+    cudaEvent_t lane_shade[PTB_MAX_LANES]{}, lane_shadow[PTB_MAX_LANES]{}, lane_join[PTB_MAX_LANES]{}, ev_fork = nullptr;
+    cudaEvent_t ev_acc[PTB_MAX_LANES]{};   // accumulate of the last chunk of each lane (chunks add to the film in Sobol order)
+    int mlt_lanes = 2;              // "mlt_lanes" / PTB_MLT_LANES: concurrent sub-populations of the MLT chains (1 = one wavefront)
+    int pt_lanes = 2;               // "pt_lanes" / PTB_PT_LANES: lanes the chunks of a multi-batch render alternate between
     bool overlap_shadow = true;     // PTB_NO_OVERLAP=1 turns the overlap off
     Ctrl* d_ctrl = nullptr;
     DevCounters* d_counters = nullptr;
@@ -227,7 +229,7 @@ inline void ptb_shade_prepare_cache(ptb_ctx* c) { c->fast_shade ? ptb_shade_prep
 inline void ptb_shade_launch(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
     c->fast_shade ? ptb_shade_launch_fast(c, L, engine, rngtab, dim, rng_stride, fm, cur, st) : ptb_shade_launch_strict(c, L, engine, rngtab, dim, rng_stride, fm, cur, st);
 }
-Lane ptb_lane(ptb_ctx* c, int which);
+Lane ptb_lane(ptb_ctx* c, int which, int nlanes);        // lane `which` of `nlanes` equal shares of the pools
 int ptb_wf_measure_l2(ptb_ctx* c, int mbytes, int iters, float* gbps);
 int ptb_wf_selftest(ptb_ctx* c, int what, long long n, unsigned long long seed, long long* fails);
 int ptb_wf_mlt_reset(ptb_ctx* c);

@@ -372,17 +372,28 @@ static void launch_extend(ptb_ctx* c, const Lane& L, const TraceScene& S, int po
 static void launch_shadow(ptb_ctx* c, const Lane& L, const TraceScene& S, int policy, cudaStream_t st, const ExpQ& tq) {
     launch_trace_io(c, S, ShadowIO{L.sq.o, L.sq.d, L.sq.c, c->st.result}, policy, 1, &L.ctrl->cur_shadow, &L.ctrl->n_shadow, st, tq, L.ctrl);
 }
-// lane 0: the context's pools and streams; lane 1: the upper half of every pool, streams 3 / 4, the second control block
-Lane ptb_lane(ptb_ctx* c, int which) {
+// lane `which` of `nlanes`: an equal share of every pool; lane 0 runs on the context's stream pair, the others on their own
+Lane ptb_lane(ptb_ctx* c, int which, int nlanes) {
     Lane L;
-    const size_t off = which ? (size_t)(c->max_paths / 2) : 0;
+    const size_t off = (size_t)(c->max_paths / nlanes) * which;
     for (int k = 0; k < 2; k++) { L.xq[k].o = c->xq[k].o + off; L.xq[k].d = c->xq[k].d + off; L.xq[k].c = nullptr; }
     L.sq.o = c->sq.o + off; L.sq.d = c->sq.d + off; L.sq.c = c->sq.c + off;
     for (int k = 0; k < PTB_EXP_K; k++) { L.tq.e[k] = c->tq.e[k] + off; L.tq2.e[k] = c->tq2.e[k] + off; }
     L.ctrl = c->d_ctrl + which;
-    L.s_main = which ? c->stream3 : c->stream; L.s_side = which ? c->stream4 : c->stream2;
-    L.ev_shade = which ? c->ev_shade1 : c->ev_shade; L.ev_shadow = which ? c->ev_shadow1 : c->ev_shadow;
+    L.s_main = which ? c->lane_main[which] : c->stream; L.s_side = which ? c->lane_side[which] : c->stream2;
+    L.ev_shade = which ? c->lane_shade[which] : c->ev_shade; L.ev_shadow = which ? c->lane_shadow[which] : c->ev_shadow;
     return L;
+}
+// lanes 1.. start after everything already enqueued on the caller's stream, and the caller's stream continues after they are done
+static int lanes_fork(ptb_ctx* c, int nlanes) {
+    if (nlanes < 2) return 0;
+    PTB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    for (int w = 1; w < nlanes; w++) PTB_CUDA(cudaStreamWaitEvent(c->lane_main[w], c->ev_fork, 0));
+    return 0;
+}
+static int lanes_join(ptb_ctx* c, int nlanes) {
+    for (int w = 1; w < nlanes; w++) { PTB_CUDA(cudaEventRecord(c->lane_join[w], c->lane_main[w])); PTB_CUDA(cudaStreamWaitEvent(c->stream, c->lane_join[w], 0)); }
+    return 0;
 }
 
 void ptb_stage_begin(ptb_ctx* c, int stage) {
@@ -418,8 +429,8 @@ int ptb_wf_init(ptb_ctx* c) {
                        &c->xq[0].o, &c->xq[0].d, &c->xq[1].o, &c->xq[1].d, &c->sq.o, &c->sq.d, &c->sq.c, &c->tq.e[0], &c->tq.e[1], &c->tq.e[2], &c->tq.e[3], &c->tq.e[4],
                        &c->tq2.e[0], &c->tq2.e[1], &c->tq2.e[2], &c->tq2.e[3], &c->tq2.e[4]};
     for (auto a : arrs) PTB_CUDA(cudaMalloc(a, sizeof(float4) * np));
-    PTB_CUDA(cudaMalloc(&c->d_ctrl, 2 * sizeof(Ctrl)));          // one control block per lane
-    PTB_CUDA(cudaMemset(c->d_ctrl, 0, 2 * sizeof(Ctrl)));
+    PTB_CUDA(cudaMalloc(&c->d_ctrl, PTB_MAX_LANES * sizeof(Ctrl)));          // one control block per lane
+    PTB_CUDA(cudaMemset(c->d_ctrl, 0, PTB_MAX_LANES * sizeof(Ctrl)));
     PTB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
     PTB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     PTB_CUDA(cudaMalloc(&c->d_params, sizeof(SceneParams)));
@@ -435,12 +446,17 @@ int ptb_wf_init(ptb_ctx* c) {
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shadow, cudaEventDisableTiming));
-    PTB_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
-    PTB_CUDA(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&c->ev_shade1, &c->ev_shadow1, &c->ev_fork, &c->ev_join}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    c->mlt_two_lanes = getenv("PTB_MLT_ONE_LANE") == nullptr;
-    c->pt_two_lanes = getenv("PTB_PT_ONE_LANE") == nullptr;
-    for (cudaEvent_t* e : {&c->ev_acc[0], &c->ev_acc[1]}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int w = 1; w < PTB_MAX_LANES; w++) {
+        PTB_CUDA(cudaStreamCreateWithFlags(&c->lane_main[w], cudaStreamNonBlocking));
+        PTB_CUDA(cudaStreamCreateWithFlags(&c->lane_side[w], cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&c->lane_shade[w], &c->lane_shadow[w], &c->lane_join[w]}) PTB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    for (int w = 0; w < PTB_MAX_LANES; w++) PTB_CUDA(cudaEventCreateWithFlags(&c->ev_acc[w], cudaEventDisableTiming));
+    PTB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    if (const char* v = getenv("PTB_MLT_LANES")) { const int k = atoi(v); if (k >= 1 && k <= PTB_MAX_LANES) c->mlt_lanes = k; }
+    if (const char* v = getenv("PTB_PT_LANES")) { const int k = atoi(v); if (k >= 1 && k <= PTB_MAX_LANES) c->pt_lanes = k; }
+    if (getenv("PTB_MLT_ONE_LANE")) c->mlt_lanes = 1;
+    if (getenv("PTB_PT_ONE_LANE")) c->pt_lanes = 1;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 1, false>, PTB_TRACE_BLK, 0));
     c->blocks_exact = c->sm_count * (occ > 0 ? occ : 4);
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_simple<ExtendIO, 0, false>, PTB_TRACE_BLK, 0));
@@ -538,13 +554,12 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
         // kernels mostly tail: the population runs as two halves on two lanes (own queues, control block and streams), which only
         // meet again when the call returns.  Splats are atomic, chain state is per chain: nothing is shared but the film.
         const int n = c->mlt_count;
-        const bool two = c->mlt_two_lanes && !c->profiling && n >= 8192 && (long long)n <= c->max_paths;
-        const int nlanes = two ? 2 : 1;
-        if (two) { PTB_CUDA(cudaEventRecord(c->ev_fork, st)); PTB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0)); }
+        const int nlanes = (c->mlt_lanes > 1 && !c->profiling && n >= 8192 && (long long)n <= c->max_paths) ? c->mlt_lanes : 1;
+        if (lanes_fork(c, nlanes)) return 1;
         for (int it = 0; it < count; it++) {
             for (int w = 0; w < nlanes; w++) {
-                const Lane L = ptb_lane(c, w);
-                const int first = w == 0 ? 0 : n / 2, cnt = two ? (w == 0 ? n / 2 : n - n / 2) : n;
+                const Lane L = ptb_lane(c, w, nlanes);
+                const int first = (int)((long long)n * w / nlanes), cnt = (int)((long long)n * (w + 1) / nlanes) - first;
                 ptb_stage_begin(c, ST_RAYGEN);
                 k_ctrl_begin<<<1, 1, 0, L.s_main>>>(L.ctrl, 0);
                 k_mlt_raygen<<<nblk(cnt), BLK, 0, L.s_main>>>(c->d_params, c->d_Xold, c->d_Xnew, first, cnt, c->mlt_first, c->mlt_seed, c->mlt_iter, c->mlt_lsp, c->mlt_sigma,
@@ -559,12 +574,11 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
             }
             c->mlt_iter++;
         }
-        if (two) { PTB_CUDA(cudaEventRecord(c->ev_join, c->stream3)); PTB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0)); }
+        if (lanes_join(c, nlanes)) return 1;
         PTB_CUDA(cudaGetLastError());
         return 0;
     }
 
-    const Lane L0 = ptb_lane(c, 0);
     int per_batch = (int)(c->max_paths / fm.pps);
     if (window && count > per_batch) { ptb_set_error("a window of %d samples needs %lld path slots, pool has %lld", count, (long long)count * fm.pps, (long long)c->max_paths); return 1; }
     if (per_batch < 1) { ptb_set_error("film %dx%d needs %d path slots per sample, pool has %lld", c->nx, c->ny, fm.pps, (long long)c->max_paths); return 1; }
@@ -572,19 +586,20 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
     // A render of several batches (config 4: 4 samples of a 1080p film fill the pool) runs its batches as half-sized chunks that
     // alternate between the two lanes: chunk b+1 traces while chunk b drains, each filling the SMs the other's persistent kernels leave
     // idle.  Chunks add to the film in Sobol order (the accumulate of chunk b waits for that of chunk b-1), so the film is bit-identical.
-    const int half = (int)((c->max_paths / 2) / fm.pps);
-    const bool two = c->pt_two_lanes && !c->profiling && !window && !sample_out_dev && engine != PTB_ENGINE_PREVIEW && count > per_batch && half >= 1;
-    const int chunk = two ? half : per_batch;
-    if (ensure_sobolP(c, two ? 2 * chunk : (count < chunk ? count : chunk))) return 1;
-    if (two) { PTB_CUDA(cudaEventRecord(c->ev_fork, st)); PTB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork, 0)); }
+    int nlanes = (c->pt_lanes > 1 && !c->profiling && !window && !sample_out_dev && engine != PTB_ENGINE_PREVIEW && count > per_batch) ? c->pt_lanes : 1;
+    while (nlanes > 1 && (c->max_paths / nlanes) / fm.pps < 1) nlanes--;
+    const bool two = nlanes > 1;
+    const int chunk = two ? (int)((c->max_paths / nlanes) / fm.pps) : per_batch;
+    if (ensure_sobolP(c, two ? nlanes * chunk : (count < chunk ? count : chunk))) return 1;
+    if (lanes_fork(c, nlanes)) return 1;
     int b = 0;
     for (int done = 0; done < count; done += chunk, b++) {
         const int ns = count - done < chunk ? count - done : chunk;
-        const int w = two ? (b & 1) : 0;
-        const Lane L = ptb_lane(c, w);
+        const int w = b % nlanes;
+        const Lane L = ptb_lane(c, w, nlanes);
         cudaStream_t ls = L.s_main;
         FrameMap lfm = fm;
-        lfm.slot_base = w ? (int)(c->max_paths / 2) : 0;
+        lfm.slot_base = (int)((c->max_paths / nlanes) * w);
         float* P = c->d_sobolP + (size_t)w * chunk * c->sobol_dim;
         ptb_stage_begin(c, ST_RAYGEN);
         k_sobol_points<<<nblk(c->sobol_dim, 256), 256, 0, ls>>>(c->d_sobolV, c->sobol_dim, window ? k_first : k_first + done * stride, window ? 1 : ns, window ? 1 : stride, P);
@@ -608,14 +623,14 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
         int rc = engine == PTB_ENGINE_PATH ? run_bounces<PTB_ENGINE_PATH>(c, L, P, c->sobol_dim, 0, lfm)
                                            : run_bounces<PTB_ENGINE_BRUTE>(c, L, P, c->sobol_dim, 0, lfm);
         if (rc) return 1;
-        if (two && b > 0) PTB_CUDA(cudaStreamWaitEvent(ls, c->ev_acc[w ^ 1], 0));       // Sobol order of the additions into the film
+        if (two && b > 0) PTB_CUDA(cudaStreamWaitEvent(ls, c->ev_acc[(w + nlanes - 1) % nlanes], 0));   // Sobol order of the additions into the film
         ptb_stage_begin(c, ST_ACCUM);
         k_accumulate<<<nblk(fm.pps), BLK, 0, ls>>>(c->d_film, c->st.result, lfm, ns, sample_out_dev);
         ptb_stage_end(c);
         if (two) PTB_CUDA(cudaEventRecord(c->ev_acc[w], ls));
         c->launches++;
     }
-    if (two) { PTB_CUDA(cudaEventRecord(c->ev_join, c->stream3)); PTB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0)); }
+    if (lanes_join(c, nlanes)) return 1;
     PTB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -628,7 +643,7 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
     if (fm.pps > c->max_paths) { ptb_set_error("film larger than the path pool"); return 1; }
     if (ensure_sobolP(c, 1)) return 1;
     if (ptb_wf_sobol_points(c, k, 1, 1, c->d_sobolP)) return 1;
-    const Lane L0 = ptb_lane(c, 0);
+    const Lane L0 = ptb_lane(c, 0, 1);
     k_ctrl_begin<<<1, 1, 0, st>>>(L0.ctrl, 0);
     k_raygen<<<c->blocks_generic, BLK, 0, st>>>(c->d_params, c->d_sobolP, c->sobol_dim, fm, 1, 1, c->st, L0.xq[0], L0.ctrl, nullptr);
     if (rays_dev) k_gather_primary<<<nblk(fm.pps), BLK, 0, st>>>(fm, c->st, rays_dev, nullptr, nullptr, nullptr, nullptr, 0);

@@ -158,7 +158,7 @@ def test_two_lane_schedules_are_bit_identical(gpu):
     neither may change a bit of the film.  1920x1080 fills the path pool with 4 samples, so 10 samples are 5 chunks on 2 lanes."""
     sc = dict(scenes.mega_small(), size=(1920, 1080))
     films = {}
-    for key, opts in (('two', {}), ('one', {'pt_two_lanes': 0}), ('lbvh', {'ploc_big': 0})):
+    for key, opts in (('two', {}), ('one', {'pt_lanes': 1}), ('four', {'pt_lanes': 4}), ('lbvh', {'ploc_big': 0})):
         for k, v in opts.items():
             gpu.set_option(k, v)
         try:
@@ -170,9 +170,10 @@ def test_two_lane_schedules_are_bit_identical(gpu):
             assert gpu.tree.trav_ploc == (0 if key == 'lbvh' else 1)
         finally:
             for k in opts:
-                gpu.set_option(k, 1)
+                gpu.set_option(k, {'pt_lanes': 2}.get(k, 1))
     assert (films['two'][..., 3] == 10).all()
-    assert np.array_equal(bits(films['two']), bits(films['one'])) and np.array_equal(bits(films['two']), bits(films['lbvh']))
+    for key in ('one', 'four', 'lbvh'):
+        assert np.array_equal(bits(films['two']), bits(films[key])), key
     scenes.apply(worker, sc)       # back to the default tree
 
 
@@ -214,6 +215,16 @@ def test_percall_render_is_coalesced(gpu):
     assert (gpu.get_film(0)[..., 3] == 2).all() and (gpu.get_film(1)[..., 3] == 1).all() and gpu.sobol_time == 67
 
 
+def _fresh_process_state(gpu):
+    """What a new process starts with (the scripts never touch these): SobolSampler.reset() (64 updates), LightPool's default point
+    light (light/__init__.py:22-28), WorldLight's 0.1 factor with the zero-initialised texture id (light/world.py:10-16)."""
+    from ptina_b200.tools import matrix as mx
+    gpu.sobol_reset()
+    worker.clear_lights()
+    worker.add_light(mx.translate((1.0, 2.0, 3.0)), np.array([32.0, 32.0, 32.0]), 0.5, 'POINT')
+    worker.set_world_light([0.1] * 4, 0)
+
+
 def test_unmodified_benchmark_script(gpu, tmp_path, capsys, monkeypatch):
     """The reference's exams/benchmark.py -- its text, unmodified (tests/golden/exams/benchmark.py.txt; tests/test_compat_cpu.py checks
     the copy against /root/reference where that exists) -- runs against the facade through the `ptina` / `taichi` compatibility
@@ -225,7 +236,7 @@ def test_unmodified_benchmark_script(gpu, tmp_path, capsys, monkeypatch):
     os.symlink(os.path.join(root, 'assets'), tmp_path / 'assets')
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(compat.PATH)
-    gpu.sobol_reset()                      # a fresh process would start here (SobolSampler.reset(): 64 updates)
+    _fresh_process_state(gpu)
     ns = compat.run_script(str(script))
     out = capsys.readouterr().out
     assert '31 samples...' in out and out.strip().endswith('sps')
@@ -255,7 +266,7 @@ def test_unmodified_benchtiles_script(gpu, tmp_path, capsys, monkeypatch):
     os.symlink(os.path.join(root, 'assets'), tmp_path / 'assets')
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(compat.PATH)
-    gpu.sobol_reset()
+    _fresh_process_state(gpu)
     ns = compat.run_script(str(script))
     assert capsys.readouterr().out.strip().endswith('sps')
     img = ns['img']

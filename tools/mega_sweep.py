@@ -36,8 +36,9 @@ def measure(label):
 
 ctx.set_option('ploc_big', 0); measure('lbvh topology')
 ctx.set_option('ploc_big', 1)
-for r in (4, 8, 16, 32, 64, 128):
+for r in (1, 2, 3, 4, 6, 8, 16):
     ctx.set_option('ploc_radius', r); measure(f'ploc radius {r}')
-ctx.set_option('ploc_radius', 16)
-ctx.set_option('pt_two_lanes', 0); measure('ploc radius 16, one lane')
-ctx.set_option('pt_two_lanes', 1)
+ctx.set_option('ploc_radius', 4)
+for k in (1, 2, 3, 4):
+    ctx.set_option('pt_lanes', k); measure(f'ploc radius 4, {k} lane(s)')
+ctx.set_option('pt_lanes', 2)

@@ -9,11 +9,14 @@ from ptina_b200 import _native, scenes, worker
 from ptina_b200.engine import MLTPathEngine
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 sc = scenes.CONFIGS['metropolis']()
 worker.init()
 ctx = _native.context()
 ctx.use_torch_stream()
 scenes.apply(worker, sc)
+if lanes:
+    ctx.set_option('mlt_lanes', lanes)
 nch = 1 << 18
 eng = MLTPathEngine(nchains=nch, seed=0)
 eng.LSP[None] = 0.25; eng.Sigma[None] = 0.01
@@ -29,5 +32,5 @@ e0.record()
 eng.render(iters)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
-print(json.dumps({'workload': f'metropolis: 978 tris, 512x512, {nch} chains x 32 dims per render()', 'ms_per_render': ms,
+print(json.dumps({'lanes': lanes or 'default (2)', 'workload': f'metropolis: 978 tris, 512x512, {nch} chains x 32 dims per render()', 'ms_per_render': ms,
                   'proposals_per_s': nch / (ms * 1e-3), 'rays_per_render': rays_per_iter, 'Mrays_per_s': rays_per_iter / (ms * 1e-3) / 1e6}))
