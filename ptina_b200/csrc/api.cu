@@ -278,6 +278,9 @@ int ptb_load_images(ptb_ctx* c, const float* texels, int64_t ntexels, const int3
         if (nx[i] <= 0 || ny[i] <= 0 || base[i] < 0 || (int64_t)base[i] + (int64_t)nx[i] * ny[i] > ntexels) { ptb_set_error("image %d outside the texel arena", i); return 1; }
         c->h_params.img_nx[i] = nx[i]; c->h_params.img_ny[i] = ny[i]; c->h_params.img_base[i] = base[i];
     }
+    // ids beyond this load are unloaded again (zero texel, ptb_shade.cuh img_fetch): the reference resets its allocators here
+    // (image.py:69-75) and sampling a stale id is undefined there
+    for (int i = nimg; i < PTB_MAX_TEXTURES; i++) { c->h_params.img_nx[i] = c->h_params.img_ny[i] = 0; c->h_params.img_base[i] = 0; }
     if (ntexels) PTB_CUDA(cudaMemcpyAsync(c->d_texels, texels, sizeof(float4) * (size_t)ntexels, memspace == PTB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->params_dirty = true;
     return 0;

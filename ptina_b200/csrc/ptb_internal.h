@@ -126,7 +126,7 @@ struct ptb_ctx {
     int *d_pl_keep = nullptr, *d_pl_make = nullptr, *d_pl_kpos = nullptr, *d_pl_mpos = nullptr, *d_pl_S = nullptr;   // multi-block PLOC (big trees)
     int pl_cap = 8200;              // entries the PLOC buffers and d_nodes2 hold
     bool ploc_big = true;           // PTB_NO_PLOC_BIG=1: trees beyond 8193 triangles keep the LBVH topology for traversal
-    int ploc_radius = 16;           // PTB_PLOC_RADIUS: search radius of the multi-block PLOC
+    int ploc_radius = 4;            // PTB_PLOC_RADIUS: search radius of the multi-block PLOC (config 4: 2..4 give the fewest node visits, tools/mega_sweep.py)
     int ploc_rounds = 0;
     bool use_ploc = true;           // PTB_NO_PLOC=1: keep the LBVH topology for traversal
     int trav_depth = -1;

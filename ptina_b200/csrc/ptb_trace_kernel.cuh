@@ -344,12 +344,24 @@ PTB_D Tri64 ld_tri_stream(const Tri64* p) {
 #define PTB_TRACE_MINB 7            /* resident CTAs per SM the global-memory variant is compiled for (72 registers) */
 #endif
 
+// The traversal stack: its first PTB_SSTACK entries live in shared memory (column = thread: no bank conflicts), deeper ones in local
+// memory.  As a local array alone (round 1) the stack was 37-39 % of the kernel's L1 sector traffic -- lanes sit at different depths,
+// so a pop pulls a 32-byte sector for 8 bytes (ncu: 2.5-2.9 bytes used per sector) -- with an L1 hit rate of 31 % (config 4) / 63 %
+// (config 2), i.e. one L2 round trip per two or three pops, and it evicted the nodes and triangles the L1 is there for.
+#ifndef PTB_SSTACK_S
+#define PTB_SSTACK_S 8              /* shared-memory stack entries per thread, resident variants (one 768-thread CTA per SM) */
+#endif
+#ifndef PTB_SSTACK_G
+#define PTB_SSTACK_G 8              /* the same for the global-memory variant (7 CTAs of 128 threads per SM) */
+#endif
 // dynamic shared memory layout of k_trace_tree (bytes), shared by the kernel and the host launch code
 template <int BLK>
 struct TraceSmem {
+    static constexpr int sstack = BLK == PTB_TRACE_BLK ? PTB_SSTACK_G : PTB_SSTACK_S;
     static constexpr size_t tile = (size_t)(BLK / 32) * 2 * PTB_EXP_K * PTB_TILE * sizeof(float4);
     static constexpr size_t queue = (size_t)PTB_PQ * BLK * (sizeof(int) + sizeof(float));
-    static constexpr size_t fixed = tile + queue;
+    static constexpr size_t stack = (size_t)sstack * BLK * sizeof(unsigned long long);
+    static constexpr size_t fixed = tile + queue + stack;
     __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64); }
     __host__ __device__ static size_t qbvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * 32; }          // quantised (Node32)
 };
@@ -378,6 +390,9 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     // pending leaves: ring of PTB_PQ (slot, lower bound of the depth) per lane, column = thread (no bank conflicts)
     int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + TraceSmem<BLK>::tile);
     float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + TraceSmem<BLK>::tile + (size_t)PTB_PQ * BLK * sizeof(int));
+    // traversal stack, entries [0, SSTACK): column = thread
+    constexpr int SSTACK = TraceSmem<BLK>::sstack;
+    unsigned long long (*s_stack)[BLK] = reinterpret_cast<unsigned long long (*)[BLK]>(s_raw + TraceSmem<BLK>::tile + TraceSmem<BLK>::queue);
     // resident nodes: quarter q of node i at s_node[q * (n-1) + i]
     float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<BLK>::fixed);
     if (SMEM) {
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     // stack entries: low word = internal node, high word = lower bound of the depth of anything below it.  A pop is issued as soon
     // as a lane runs out of children (end of its node step) into `pe`, and consumed at the start of its next node step, so the
     // local-memory load has a whole iteration to land.
-    unsigned long long stack[PTB_STACK];
+    unsigned long long stack[PTB_STACK - SSTACK > 0 ? PTB_STACK - SSTACK : 1];      // entries beyond the shared-memory part
     unsigned long long pe = 0;                 // popped entry, valid iff `popped`
     bool popped = false;
     int sp = 0;
@@ -519,14 +534,16 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     const bool first1 = !(n0 < n1);     // nearer first
                     if (d0 && d1) {
                         // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
-                        stack[sp++] = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
+                        const unsigned long long entry = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
+                        if (sp < SSTACK) s_stack[sp][threadIdx.x] = entry; else stack[sp - SSTACK] = entry;
+                        sp++;
                         if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
                         cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
                     } else if (d0) { cur = c0 - n; cur_near = n0; }
                     else if (d1) { cur = c1 - n; cur_near = n1; }
                     else cur = -1;
                 }
-                if (cur == -1 && sp > 0) { pe = stack[--sp]; popped = true; }      // out of children: issue the pop now
+                if (cur == -1 && sp > 0) { --sp; pe = sp < SSTACK ? s_stack[sp][threadIdx.x] : stack[sp - SSTACK]; popped = true; }      // out of children: issue the pop now
             }
         } else {
             // ---- leaf step: the oldest pending leaf of every lane that has one ---------------------------------------------------------------

@@ -216,9 +216,12 @@ def test_percall_render_is_coalesced(gpu):
 
 
 def _fresh_process_state(gpu):
-    """What a new process starts with (the scripts never touch these): SobolSampler.reset() (64 updates), LightPool's default point
-    light (light/__init__.py:22-28), WorldLight's 0.1 factor with the zero-initialised texture id (light/world.py:10-16)."""
+    """What a new process starts with (the scripts never touch these): zeroed material tables and no images, SobolSampler.reset()
+    (64 updates), LightPool's default point light (light/__init__.py:22-28), WorldLight's 0.1 factor with the zero-initialised texture id (light/world.py:10-16)."""
     from ptina_b200.tools import matrix as mx
+    from ptina_b200.mtllib import MaterialPool
+    MaterialPool().fac[:] = 0; MaterialPool().tex[:] = 0      # the zero-initialised tables a short (glTF, 3-slot) material list leaves alone
+    worker.load_images([])
     gpu.sobol_reset()
     worker.clear_lights()
     worker.add_light(mx.translate((1.0, 2.0, 3.0)), np.array([32.0, 32.0, 32.0]), 0.5, 'POINT')
