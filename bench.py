@@ -404,6 +404,31 @@ class Bench:
                 'parity': 'chain trajectories unpinned (ti.random); per-chain radiance, accept/reject and splats are checked in tests/test_gpu_parity.py::test_mlt_engine'}
 
 
+def issue_roofline(scene, spp_per_step, ms_per_step, sm_mhz):
+    """What binds the small-scene configs is instruction issue (nodes in shared memory, triangles in L1).  Roof = 4 warp instructions
+    per clock per SM x 148 SMs x the SM clock sampled during the timed region.  Warp instructions per step are a property of the
+    deterministic workload: counted once per build with ncu (smsp__inst_executed.sum over every launch of one step: `bench.py --one-step`,
+    tools/ncu_inst_counts.py -> profiles/inst_counts.json) and divided here by the LIVE step time."""
+    sm_mhz = sm_mhz or 1965
+    peak = 4.0 * 148 * sm_mhz * 1e6 / 1e9            # G warp-instructions / s
+    out = {'bound': 'issue', 'unit': 'Gwarp-inst/s', 'peak': peak, 'peak_source': f'4 warp-instr/clk/SM x 148 SMs x {sm_mhz} MHz (SM clock sampled during the timed region)',
+           'kernel': 'whole step (k_trace_pre + k_trace_tree + k_shade are 97 % of it)', 'timing': 'CUDA events over the timed region (ms_per_step)'}
+    inst = {}
+    try:
+        inst = json.load(open(os.path.join(ROOT, 'profiles', 'inst_counts.json'))).get(scene, {})
+    except Exception:
+        pass
+    if inst.get('warp_inst_per_step') and inst.get('spp'):
+        w = inst['warp_inst_per_step'] * spp_per_step / inst['spp']         # instructions scale with the samples of a step
+        ach = w / (ms_per_step * 1e-3) / 1e9
+        lanes = inst['thread_inst_per_step'] / inst['warp_inst_per_step']
+        out.update({'achieved': ach, 'frac': ach / peak, 'warp_inst_per_step': w, 'lanes_per_inst': lanes, 'frac_lane_weighted': ach / peak * lanes / 32.0,
+                    'inst_source': inst.get('source'), 'traffic': inst.get('dram_bytes_per_step', 0) * spp_per_step / inst['spp'], 'per_kernel': inst.get('per_kernel')})
+    else:
+        out.update({'achieved': None, 'frac': None, 'traffic': None, 'note': 'profiles/inst_counts.json has no entry for this scene'})
+    return out
+
+
 def run_gpu(args):
     B = Bench(args)
     torch, ctx, worker, native = B.torch, B.ctx, B.worker, B.native
@@ -580,27 +605,13 @@ def run_gpu(args):
         except Exception:
             pass
         hbm_peak, peak_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json)') if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md)')
-        # What binds config 2 is instruction issue (the scene is 125 KB: nodes in shared memory, triangles in L1).  Roof = 4 warp
-        # instructions per clock per SM x SMs x the SM clock sampled during the timed region.  Warp instructions per step are a property
-        # of the (deterministic) workload: counted once with ncu (smsp__inst_executed.sum over every launch of one step, tools/
-        # ncu_inst_counts.py -> profiles/inst_counts.json) and divided here by the LIVE step time.
-        inst = {}
-        try:
-            inst = json.load(open(os.path.join(ROOT, 'profiles', 'inst_counts.json'))).get(sc['name'], {})
-        except Exception:
-            pass
-        sm_mhz = clocks.get('sm_mhz') or 1965
-        issue_peak = 4.0 * 148 * sm_mhz * 1e6 / 1e9            # G warp-instructions / s
-        roofline = {'bound': 'issue', 'unit': 'Gwarp-inst/s', 'peak': issue_peak, 'peak_source': f'4 warp-instr/clk/SM x 148 SMs x {sm_mhz} MHz (SM clock sampled during the timed region)',
-                    'kernel': 'whole step (k_trace_pre + k_trace_tree + k_shade are 97 % of it)', 'timing': 'CUDA events over the timed region (ms_per_step)'}
-        if inst.get('warp_inst_per_step') and inst.get('spp') == spp:
-            ach = inst['warp_inst_per_step'] / (head['ms_per_step'] * 1e-3) / 1e9
-            lanes = inst['thread_inst_per_step'] / inst['warp_inst_per_step']
-            roofline.update({'achieved': ach, 'frac': ach / issue_peak, 'warp_inst_per_step': inst['warp_inst_per_step'], 'lanes_per_inst': lanes,
-                             'frac_lane_weighted': ach / issue_peak * lanes / 32.0, 'inst_source': inst.get('source'),
-                             'traffic': inst.get('dram_bytes_per_step'), 'per_kernel': inst.get('per_kernel')})
-        else:
-            roofline.update({'achieved': None, 'frac': None, 'traffic': None, 'note': 'profiles/inst_counts.json has no entry for this scene / spp'})
+        roofline = issue_roofline(sc['name'], spp, head['ms_per_step'], clocks.get('sm_mhz'))
+        if configs is not None:
+            for key, name in (('config1_cornell_boxes', 'cornell_boxes'), ('config3_matball', 'matball')):
+                if key in configs:
+                    r = issue_roofline(name, configs[key]['spp_per_step_total'] / world, configs[key]['ms_per_step'], clocks.get('sm_mhz'))   # per GPU
+                    r.pop('per_kernel', None)
+                    configs[key]['roofline'] = r
         # the schema's HBM view of the traversal stages, with SURVEY 8(d)'s formula (served from shared memory / L1, so not the binding roof)
         trav_ms = stage['extend'] + stage['shadow']
         alg = 64.0 * cnt['node_visits'] + 48.0 * cnt['tri_tests'] + 48.0 * cnt['rays']
