@@ -279,19 +279,23 @@ class Bench:
         return {k: v / nprof for k, v in stage.items()}
 
     def split_times(self, eng, total, reps=3):
-        """render and reduce timed separately (events around each), max over ranks: what a sharded step is made of"""
+        """render and reduce timed separately, max over ranks: what a sharded step is made of.  The ranks are re-aligned (device
+        synchronise + barrier) between the two, so `reduce_ms` is the collective itself (staging copy + ncclReduce), not the wait for
+        the slowest rank's render -- that wait is part of `render_ms` (max over ranks)."""
         ctx, pdist = self.ctx, self.pdist
         frame_nr = self.make_frame(eng, total, reduce=False)
-        a, b, c = self.event(), self.event(), self.event()
+        a, b, c, d = self.event(), self.event(), self.event(), self.event()
         r_ms = d_ms = 0.0
         for _ in range(reps):
             self.barrier()
             a.record(); frame_nr(); ctx.flush(); b.record()
+            self.barrier()
+            c.record()
             if self.world > 1:
                 pdist.reduce_film_pass(0, 0)
-            c.record()
+            d.record()
             self.barrier()
-            r_ms += self.max_over_ranks(a.elapsed_time(b)); d_ms += self.max_over_ranks(b.elapsed_time(c))
+            r_ms += self.max_over_ranks(a.elapsed_time(b)); d_ms += self.max_over_ranks(c.elapsed_time(d))
         return r_ms / reps, d_ms / reps
 
     def film_check(self, eng, total):

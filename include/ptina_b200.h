@@ -94,7 +94,7 @@ int ptb_set_mode(ptb_ctx* ctx, int mode);                           /* PTB_MODE_
 int ptb_get_mode(ptb_ctx* ctx, int* mode);
 /* scheduling / builder switches that do NOT change results (tests and measurements flip them at run time; the environment variables of
  * INTEGRATION.md section 3 set their defaults): "coalesce", "overlap_shadow", "pt_lanes" and "mlt_lanes" (1..4), "use_ploc", "ploc_big",
- * "ploc_radius".  The tree options take effect at the next ptb_build_tree. */
+ * "ploc_radius", "wide4" (4-wide nodes for trees walked out of global memory).  The tree options take effect at the next ptb_build_tree. */
 int ptb_set_option(ptb_ctx* ctx, const char* name, int value);
 int ptb_synchronize(ptb_ctx* ctx);                                  /* worker.py:17-18 */
 int ptb_flush(ptb_ctx* ctx);                                        /* submit recorded ptb_render calls without waiting */

@@ -16,6 +16,7 @@ TraceScene ptb_trace_scene(const ptb_ctx* c) {
     TraceScene S;
     S.nodes = c->d_nodes_active ? c->d_nodes_active : c->d_nodes; S.tris = c->d_tris; S.leaf = c->d_leaf; S.slot_of = c->d_slot_of; S.gate = c->d_gate; S.gbox = c->d_gbox; S.tlo = c->d_tlo; S.thi = c->d_thi; S.nlo = c->d_nlo; S.nhi = c->d_nhi; S.list = c->d_list; S.nlist = c->list_n; S.scene_abs = c->scene_abs; S.root_must = c->root_must; S.bmin = c->d_bmin; S.bmax = c->d_bmax; S.child = c->d_child; S.n = c->tree_n;
     S.qnodes = c->d_qnodes;
+    S.wnodes = (c->wide4 && c->wnodes_ok) ? c->d_wnodes : nullptr;
     for (int k = 0; k < 3; k++) { S.qbase[k] = c->qbase[k]; S.qext[k] = c->qext[k]; S.qinv[k] = c->qinv[k]; }
     return S;
 }
@@ -92,7 +93,7 @@ static int flush_pending(ptb_ctx* c) {
 // frees everything a context owns (also the partly built context of a failed ptb_create)
 static void release_ctx(ptb_ctx* c) {
     void* ptrs[] = {c->d_verts, c->d_mtlids, c->d_texels, c->d_params, c->d_cache, c->d_sobolV, c->d_sobolP, c->d_mc, c->d_id, c->d_mc_tmp, c->d_id_tmp, c->d_leaf,
-                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_nodes2, c->d_pl_id[0], c->d_pl_id[1], c->d_pl_depth[0], c->d_pl_depth[1], c->d_pl_nn, c->d_pl_lo[0], c->d_pl_lo[1], c->d_pl_hi[0], c->d_pl_hi[1], c->d_pl_keep, c->d_pl_make, c->d_pl_kpos, c->d_pl_mpos, c->d_pl_S, c->d_qnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
+                    c->d_child, c->d_bmin, c->d_bmax, c->d_ready, c->d_parentcnt, c->d_range, c->d_height, c->d_nodes, c->d_nodes2, c->d_pl_id[0], c->d_pl_id[1], c->d_pl_depth[0], c->d_pl_depth[1], c->d_pl_nn, c->d_pl_lo[0], c->d_pl_lo[1], c->d_pl_hi[0], c->d_pl_hi[1], c->d_pl_keep, c->d_pl_make, c->d_pl_kpos, c->d_pl_mpos, c->d_pl_S, c->d_qnodes, c->d_wnodes, c->d_tris, c->d_slot_of, c->d_gate, c->d_gbox, c->d_tlo, c->d_thi, c->d_nlo, c->d_nhi, c->d_list, c->d_sort_tmp, c->d_scalars,
                     c->d_film, c->st.ray_o, c->st.ray_d, c->st.hit, c->st.thr, c->st.result, c->xq[0].o, c->xq[0].d, c->xq[1].o, c->xq[1].d, c->sq.o, c->sq.d, c->sq.c, c->tq.e[0], c->tq.e[1], c->tq.e[2], c->tq.e[3], c->tq.e[4], c->tq2.e[0], c->tq2.e[1], c->tq2.e[2], c->tq2.e[3], c->tq2.e[4],
                     c->d_ctrl, c->d_counters, c->d_Xold, c->d_Xnew, c->d_Lold, c->d_resolve, c->d_flags};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -199,6 +200,7 @@ int ptb_set_option(ptb_ctx* c, const char* name, int value) {
         if (value < 1 || value > PTB_MAX_LANES) { ptb_set_error("%s outside [1, %d]", k.c_str(), PTB_MAX_LANES); return 1; }
         (k == "pt_lanes" ? c->pt_lanes : c->mlt_lanes) = value;
     }
+    else if (k == "wide4") c->wide4 = value != 0;
     else if (k == "use_ploc") c->use_ploc = value != 0;
     else if (k == "ploc_big") c->ploc_big = value != 0;
     else if (k == "ploc_radius") { if (value < 1 || value > 1024) { ptb_set_error("ploc_radius outside [1, 1024]"); return 1; } c->ploc_radius = value; }

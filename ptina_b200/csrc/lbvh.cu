@@ -625,6 +625,56 @@ __global__ void __launch_bounds__(BLK) k_quant_nodes(const Node64* __restrict__ 
     qnodes[2 * i + 1] = make_uint4(f[8] | (f[9] << 16), f[10] | (f[11] << 16), (unsigned)id0, (unsigned)id1);
 }
 
+// 4-wide quantised node of binary node i (64 B): its two children, each internal one replaced by ITS two children -- up to four
+// (box, id) entries on the same 15-bit grid as Node32 (three words per box, low half first: (lo.x lo.y) (lo.z hi.x) (hi.y hi.z)), then
+// the four ids (-1: none).  Every binary node gets one (index = binary index); a traversal from the root only ever reaches those at
+// even depth, so the hot footprint equals the binary quantised array's.
+__global__ void __launch_bounds__(BLK) k_wide4_nodes(const Node64* __restrict__ nodes, int n, QuantGrid g, uint4* __restrict__ wnodes, int* __restrict__ scal) {
+    int i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= n - 1) return;
+    const Node64 N = nodes[i];
+    float lo[4][3], hi[4][3]; int id[4]; int m = 0;
+    const int cid[2] = {__float_as_int(N.a.w), __float_as_int(N.b.w)};
+    const float4 clo[2] = {N.a, N.c}, chi[2] = {N.b, N.d};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (cid[k] < 0) continue;
+        const int c = cid[k] & PTB_NODE_ID;
+        if (c < n) {                                       // leaf: itself
+            lo[m][0] = clo[k].x; lo[m][1] = clo[k].y; lo[m][2] = clo[k].z; hi[m][0] = chi[k].x; hi[m][1] = chi[k].y; hi[m][2] = chi[k].z; id[m++] = cid[k];
+        } else {                                           // internal: its children (their own ids carry their own flags)
+            const Node64 M = nodes[c - n];
+            const int gid[2] = {__float_as_int(M.a.w), __float_as_int(M.b.w)};
+            const float4 glo[2] = {M.a, M.c}, ghi[2] = {M.b, M.d};
+            int took = 0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (gid[j] < 0) continue;
+                lo[m][0] = glo[j].x; lo[m][1] = glo[j].y; lo[m][2] = glo[j].z; hi[m][0] = ghi[j].x; hi[m][1] = ghi[j].y; hi[m][2] = ghi[j].z; id[m++] = gid[j]; took++;
+            }
+            (void)took;
+        }
+    }
+    unsigned w[16];
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool used = k < m;
+        unsigned f[6];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            int dummy = 0;
+            f[a] = quant_plane(used ? lo[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], false, used ? &bad : &dummy);
+            f[3 + a] = quant_plane(used ? hi[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], true, used ? &bad : &dummy);
+        }
+        w[3 * k] = f[0] | (f[1] << 16); w[3 * k + 1] = f[2] | (f[3] << 16); w[3 * k + 2] = f[4] | (f[5] << 16);
+        w[12 + k] = used ? (unsigned)id[k] : 0xFFFFFFFFu;
+    }
+    if (bad) atomicAdd(&scal[14], 1);
+#pragma unroll
+    for (int q = 0; q < 4; q++) wnodes[4 * (size_t)i + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
 // packed 64-byte triangle by leaf slot; u, v, n, uu, uv, vv, D are the f32 expressions of geometries.py:121-141
 __global__ void __launch_bounds__(BLK) k_pack_tris(const float* __restrict__ verts, const int* __restrict__ leaf, int n, Tri64* tris, int* slot_of) {
     int s = blockIdx.x * BLK + threadIdx.x;
@@ -842,9 +892,23 @@ int ptb_lbvh_build(ptb_ctx* c) {
                 finite = finite && std::isfinite(c->qext[k]) && std::isfinite(c->qinv[k]) && c->qinv[k] > 0.0f;
             }
             int bad = 1;
+            c->wnodes_ok = false;
             if (finite) {
                 k_quant_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_nodes_active, n, g, c->d_qnodes, c->d_scalars);
                 c->launches++;
+                // 4-wide nodes for a tree walked out of global memory; three stack pushes per step: height <= 40 keeps the 64-entry stack safe
+                const int tdepth = c->d_nodes_active == c->d_nodes2 ? c->trav_depth : depth;
+                if (c->wide4 && ptb_tree_mode(c, n) == PTB_TREE_GLOBAL && tdepth >= 1 && tdepth <= 40) {
+                    if (c->wnodes_cap < n) {
+                        PTB_CUDA(cudaStreamSynchronize(st));
+                        cudaFree(c->d_wnodes); c->d_wnodes = nullptr;
+                        PTB_CUDA(cudaMalloc((void**)&c->d_wnodes, sizeof(uint4) * 4 * (size_t)n));
+                        c->wnodes_cap = n;
+                    }
+                    k_wide4_nodes<<<nblk(n - 1), BLK, 0, st>>>(c->d_nodes_active, n, g, c->d_wnodes, c->d_scalars);
+                    c->launches++;
+                    c->wnodes_ok = true;
+                }
                 PTB_CUDA(cudaMemcpyAsync(&bad, &c->d_scalars[14], sizeof(int), cudaMemcpyDeviceToHost, st));
                 PTB_CUDA(cudaStreamSynchronize(st));
             }

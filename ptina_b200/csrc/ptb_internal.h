@@ -131,6 +131,9 @@ struct ptb_ctx {
     bool use_ploc = true;           // PTB_NO_PLOC=1: keep the LBVH topology for traversal
     int trav_depth = -1;
     uint4* d_qnodes = nullptr;      // [2(n-1)] quantised copy of d_nodes (Node32), built for trees that are traversed out of global memory
+    uint4* d_wnodes = nullptr;      // [4(n-1)] 4-wide quantised nodes (lbvh.cu k_wide4_nodes), global-memory trees only
+    int wnodes_cap = 0; bool wnodes_ok = false;
+    bool wide4 = true;              // "wide4" / PTB_NO_WIDE4=1: walk big trees through the 4-wide nodes
     float qbase[3]{}, qext[3]{1.0f, 1.0f, 1.0f}, qinv[3]{1.0f, 1.0f, 1.0f};
     Tri64* d_tris = nullptr;
     int32_t* d_slot_of = nullptr;   // face id -> leaf slot

@@ -355,11 +355,12 @@ PTB_D Tri64 ld_tri_stream(const Tri64* p) {
 #define PTB_SSTACK_G 8              /* the same for the global-memory variant (7 CTAs of 128 threads per SM) */
 #endif
 // dynamic shared memory layout of k_trace_tree (bytes), shared by the kernel and the host launch code
-template <int BLK>
+template <int BLK, bool W4 = false>
 struct TraceSmem {
     static constexpr int sstack = BLK == PTB_TRACE_BLK ? PTB_SSTACK_G : PTB_SSTACK_S;
+    static constexpr int pq = W4 ? 2 * PTB_PQ : PTB_PQ;     // pending-leaf ring entries per lane (a 4-wide node step can add four)
     static constexpr size_t tile = (size_t)(BLK / 32) * 2 * PTB_EXP_K * PTB_TILE * sizeof(float4);
-    static constexpr size_t queue = (size_t)PTB_PQ * BLK * (sizeof(int) + sizeof(float));
+    static constexpr size_t queue = (size_t)pq * BLK * (sizeof(int) + sizeof(float));
     static constexpr size_t stack = (size_t)sstack * BLK * sizeof(unsigned long long);
     static constexpr size_t fixed = tile + queue + stack;
     __host__ __device__ static size_t bvh(int n) { return (size_t)(n > 1 ? n - 1 : 0) * sizeof(Node64); }
@@ -373,8 +374,13 @@ struct TraceSmem {
 // L1 wavefront per lane and 16-byte load.  Triangles, gate boxes and the local-memory stack stay behind L1, which keeps ~100 KB
 // next to the carve-out.  SMEM = false (bigger trees): quantised nodes out of global memory, one 256-bit load per step, several
 // CTAs per SM to cover the L2 latency.
-template <class IO, bool COUNT, int BLK, bool SMEM, bool QN>
+// W4 (global-memory variant only): 4-wide quantised nodes (lbvh.cu k_wide4_nodes: a binary node with its internal children replaced by
+// their children, 64 bytes) -- half as many dependent node fetches per ray, which is what the big-scene kernel waits for.
+template <class IO, bool COUNT, int BLK, bool SMEM, bool QN, bool W4 = false>
 __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(TraceScene S, IO io, ExpQ xq, int* cursor, const int* count_ptr, DevCounters* ctr) {
+    static_assert(!W4 || (!SMEM && QN), "4-wide nodes: global-memory quantised variant only");
+    using Smem = TraceSmem<BLK, W4>;
+    constexpr int PQ = Smem::pq;
     constexpr bool ANYHIT = IO::kAnyHit;
     constexpr int K = PTB_EXP_K;
     constexpr unsigned FULL = 0xffffffffu;
@@ -388,13 +394,13 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     // staged ray records: [warp][buffer][k][record]
     float4 (*s_tile)[2][K][PTB_TILE] = reinterpret_cast<float4 (*)[2][K][PTB_TILE]>(s_raw);
     // pending leaves: ring of PTB_PQ (slot, lower bound of the depth) per lane, column = thread (no bank conflicts)
-    int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + TraceSmem<BLK>::tile);
-    float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + TraceSmem<BLK>::tile + (size_t)PTB_PQ * BLK * sizeof(int));
+    int (*s_qslot)[BLK] = reinterpret_cast<int (*)[BLK]>(s_raw + Smem::tile);
+    float (*s_qnear)[BLK] = reinterpret_cast<float (*)[BLK]>(s_raw + Smem::tile + (size_t)PQ * BLK * sizeof(int));
     // traversal stack, entries [0, SSTACK): column = thread
-    constexpr int SSTACK = TraceSmem<BLK>::sstack;
-    unsigned long long (*s_stack)[BLK] = reinterpret_cast<unsigned long long (*)[BLK]>(s_raw + TraceSmem<BLK>::tile + TraceSmem<BLK>::queue);
+    constexpr int SSTACK = Smem::sstack;
+    unsigned long long (*s_stack)[BLK] = reinterpret_cast<unsigned long long (*)[BLK]>(s_raw + Smem::tile + Smem::queue);
     // resident nodes: quarter q of node i at s_node[q * (n-1) + i]
-    float4* s_node = reinterpret_cast<float4*>(s_raw + TraceSmem<BLK>::fixed);
+    float4* s_node = reinterpret_cast<float4*>(s_raw + Smem::fixed);
     if (SMEM) {
         if (blockIdx.x * PTB_TILE >= count) return;        // more CTAs than tiles of work: skip the copy
         if constexpr (QN) {                                 // quantised nodes: two 16-byte halves per node
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     while (true) {
         // a lane can take a node step if it has a node (current or stacked) and room for two more pending leaves; a leaf step if
         // a leaf is pending.  A lane with neither is idle: finished (result not stored yet) or never started.
-        const bool node_ok = (cur != -1 || popped) && q_count <= PTB_PQ - 2;
+        const bool node_ok = (cur != -1 || popped) && q_count <= PQ - (W4 ? 4 : 2);
         const bool leaf_ok = q_count > 0;
         const unsigned mn = __ballot_sync(FULL, node_ok), ml = __ballot_sync(FULL, leaf_ok);
         const unsigned idle = ~(mn | ml);
@@ -499,10 +505,45 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
             // ---- node step: one 64-byte node, both children's slab tests ----------------------------------------------------------------------
 #pragma unroll 1
             for (int rep = 0; rep < PTB_NODE_REPS; rep++)
-            if (rep == 0 ? node_ok : ((cur != -1 || popped) && q_count <= PTB_PQ - 2)) {
+            if (rep == 0 ? node_ok : ((cur != -1 || popped) && q_count <= PQ - (W4 ? 4 : 2))) {
                 if (cur == -1) { cur = (int)(unsigned)pe; cur_near = __int_as_float((int)(pe >> 32)); popped = false; }
                 if (cur_near > cull) cur = -1;          // nothing below can beat the best hit found since it was pushed / chosen
-                else {
+                else if constexpr (W4) {
+                    uint4 qa, qb, qc, qd;
+                    ld_qnode256(S.wnodes + 4 * (size_t)cur, &qa, &qb); ld_qnode256(S.wnodes + 4 * (size_t)cur + 2, &qc, &qd);
+                    const unsigned bw[12] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, qc.x, qc.y, qc.z, qc.w};
+                    const int wid[4] = {(int)qd.x, (int)qd.y, (int)qd.z, (int)qd.w};
+                    if (COUNT) { C.nodes++; C.boxes += 4; }
+                    float nn[4]; int cc[4];
+                    int m = 0;                              // internal children hit
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float nk;
+                        bool hk = slab_quant(quant_lo(bw[3 * k]), quant_hi(bw[3 * k]), quant_lo(bw[3 * k + 1]), quant_hi(bw[3 * k + 1]), quant_lo(bw[3 * k + 2]), quant_hi(bw[3 * k + 2]), G, R.a2, &nk);
+                        hk = hk && wid[k] >= 0;
+                        const int ck = wid[k] & PTB_NODE_ID;
+                        if (wid[k] & PTB_NODE_MUST) nk = 0.0f;        // an ill-conditioned triangle below: no distance bound holds
+                        hk = hk && !(nk > cull);
+                        const bool leafk = ck < n;
+                        if (hk && leafk && ck != avoid_slot) { const int q = (q_head + q_count) & (PQ - 1); s_qslot[q][threadIdx.x] = ck; s_qnear[q][threadIdx.x] = nk; q_count++; }
+                        const bool dk = hk && !leafk;
+                        nn[k] = dk ? nk : 3.0e38f; cc[k] = ck - n;
+                        m += dk ? 1 : 0;
+                    }
+                    // nearest first: sort the four (near, node) pairs (misses carry +huge), 5 compare-exchanges
+#define PTB_CSWAP(a, b) { const bool sw = nn[b] < nn[a]; const float tn = sw ? nn[a] : nn[b]; const int tc = sw ? cc[a] : cc[b]; nn[a] = sw ? nn[b] : nn[a]; cc[a] = sw ? cc[b] : cc[a]; nn[b] = tn; cc[b] = tc; }
+                    PTB_CSWAP(0, 1) PTB_CSWAP(2, 3) PTB_CSWAP(0, 2) PTB_CSWAP(1, 3) PTB_CSWAP(1, 2)
+#undef PTB_CSWAP
+                    // farther ones onto the stack, farthest first; the nearest is next (a proper tree of height <= 40 cannot overflow: checked by the host)
+#pragma unroll
+                    for (int k = 3; k >= 1; k--) if (k < m) {
+                        const unsigned long long entry = ((unsigned long long)(unsigned)__float_as_int(nn[k]) << 32) | (unsigned)cc[k];
+                        if (sp < SSTACK) s_stack[sp][threadIdx.x] = entry; else stack[sp - SSTACK] = entry;
+                        sp++;
+                    }
+                    if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
+                    if (m > 0) { cur = cc[0]; cur_near = nn[0]; } else cur = -1;
+                } else {
                     int w0, w1;                          // child ids; -1: nothing below
                     float n0, n1;
                     bool h0, h1;
@@ -528,8 +569,8 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     h0 = h0 && !(n0 > cull); h1 = h1 && !(n1 > cull);
                     const bool leaf0 = c0 < n, leaf1 = c1 < n;
                     const bool p0 = h0 && leaf0 && c0 != avoid_slot, p1 = h1 && leaf1 && c1 != avoid_slot;
-                    if (p0) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c0; s_qnear[k][threadIdx.x] = n0; q_count++; }
-                    if (p1) { const int k = (q_head + q_count) & (PTB_PQ - 1); s_qslot[k][threadIdx.x] = c1; s_qnear[k][threadIdx.x] = n1; q_count++; }
+                    if (p0) { const int k = (q_head + q_count) & (PQ - 1); s_qslot[k][threadIdx.x] = c0; s_qnear[k][threadIdx.x] = n0; q_count++; }
+                    if (p1) { const int k = (q_head + q_count) & (PQ - 1); s_qslot[k][threadIdx.x] = c1; s_qnear[k][threadIdx.x] = n1; q_count++; }
                     const bool d0 = h0 && !leaf0, d1 = h1 && !leaf1;
                     const bool first1 = !(n0 < n1);     // nearer first
                     if (d0 && d1) {
@@ -549,7 +590,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
             // ---- leaf step: the oldest pending leaf of every lane that has one ---------------------------------------------------------------
             if (leaf_ok) {
                 const int slot = s_qslot[q_head][threadIdx.x]; const float lnear = s_qnear[q_head][threadIdx.x];
-                q_head = (q_head + 1) & (PTB_PQ - 1); q_count--;
+                q_head = (q_head + 1) & (PQ - 1); q_count--;
                 if (!(lnear > cull)) {
                     const Tri64 T = (!SMEM && PTB_STREAM_TRIS) ? ld_tri_stream(S.tris + slot) : S.tris[slot];
                     if (COUNT) C.tris++;

@@ -58,6 +58,7 @@ struct TraceScene {
     int n;
     // quantised copy of `nodes` for trees that do not fit in shared memory (32 B per node, see Node32)
     const uint4* __restrict__ qnodes;    // [2(n-1)]
+    const uint4* __restrict__ wnodes;    // [4(n-1)] 4-wide quantised nodes (64 B: 12 box words + 4 child ids), or NULL
     float qbase[3], qext[3], qinv[3];    // plane = qbase + v * qext, v in [1, 2) on a 15-bit grid; qext a power of two, qinv = 1 / qext
 };
 

@@ -358,6 +358,9 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
             auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
             kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
+        } else if (S.wnodes) {
+            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK, false, true, true>;
+            kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK, true>::fixed, st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else {
             auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK, false, true>;
             kern<<<c->sm_count * PTB_TRACE_MINB, PTB_TRACE_BLK, TraceSmem<PTB_TRACE_BLK>::fixed, st>>>(S, io, tq, cur_tree, n_tree, ctr);
@@ -442,6 +445,7 @@ int ptb_wf_init(ptb_ctx* c) {
     c->overlap_shadow = getenv("PTB_NO_OVERLAP") == nullptr;
     c->use_ploc = getenv("PTB_NO_PLOC") == nullptr;
     c->ploc_big = getenv("PTB_NO_PLOC_BIG") == nullptr;
+    c->wide4 = getenv("PTB_NO_WIDE4") == nullptr;
     if (const char* r = getenv("PTB_PLOC_RADIUS")) { const int v = atoi(r); if (v >= 1 && v <= 1024) c->ploc_radius = v; }
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));

@@ -154,11 +154,12 @@ def test_config4_full_size_against_oracle(gpu):
 
 
 def test_two_lane_schedules_are_bit_identical(gpu):
-    """Multi-batch renders alternate half-sized chunks between two lanes, and the big-tree PLOC rebuild changes the traversal tree:
-    neither may change a bit of the film.  1920x1080 fills the path pool with 4 samples, so 10 samples are 5 chunks on 2 lanes."""
+    """Multi-batch renders alternate half-sized chunks between two lanes, the big-tree PLOC rebuild changes the traversal tree, and trees
+    walked out of global memory use 4-wide nodes: none of it may change a bit of the film (PTB_NO_RESIDENT_BVH=1 runs of the suite put
+    every scene through the global-memory kernel).  1920x1080 fills the path pool with 4 samples, so 10 samples are 5 chunks on 2 lanes."""
     sc = dict(scenes.mega_small(), size=(1920, 1080))
     films = {}
-    for key, opts in (('two', {}), ('one', {'pt_lanes': 1}), ('four', {'pt_lanes': 4}), ('lbvh', {'ploc_big': 0})):
+    for key, opts in (('two', {}), ('one', {'pt_lanes': 1}), ('four', {'pt_lanes': 4}), ('lbvh', {'ploc_big': 0}), ('binary', {'wide4': 0})):
         for k, v in opts.items():
             gpu.set_option(k, v)
         try:
@@ -172,7 +173,7 @@ def test_two_lane_schedules_are_bit_identical(gpu):
             for k in opts:
                 gpu.set_option(k, {'pt_lanes': 2}.get(k, 1))
     assert (films['two'][..., 3] == 10).all()
-    for key in ('one', 'four', 'lbvh'):
+    for key in ('one', 'four', 'lbvh', 'binary'):
         assert np.array_equal(bits(films['two']), bits(films[key])), key
     scenes.apply(worker, sc)       # back to the default tree
 

@@ -34,11 +34,9 @@ def measure(label):
                       'tris_per_ray': round(c['tri_tests'] / c['rays'], 2), 'build_ms': round(info.build_ms, 2), 'trav_depth': info.trav_depth, 'ploc': info.trav_ploc}), flush=True)
 
 
-ctx.set_option('ploc_big', 0); measure('lbvh topology')
-ctx.set_option('ploc_big', 1)
-for r in (1, 2, 3, 4, 6, 8, 16):
-    ctx.set_option('ploc_radius', r); measure(f'ploc radius {r}')
-ctx.set_option('ploc_radius', 4)
-for k in (1, 2, 3, 4):
-    ctx.set_option('pt_lanes', k); measure(f'ploc radius 4, {k} lane(s)')
-ctx.set_option('pt_lanes', 2)
+for wide in (0, 1):
+    ctx.set_option('wide4', wide)
+    measure(f'ploc r4, 2 lanes, wide4={wide}')
+ctx.set_option('wide4', 1)
+ctx.set_option('ploc_big', 0); measure('lbvh topology, wide4=1'); ctx.set_option('ploc_big', 1)
+ctx.set_option('pt_lanes', 1); measure('ploc r4, 1 lane, wide4=1'); ctx.set_option('pt_lanes', 2)
