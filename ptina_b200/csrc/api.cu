@@ -201,6 +201,7 @@ int ptb_set_option(ptb_ctx* c, const char* name, int value) {
         (k == "pt_lanes" ? c->pt_lanes : c->mlt_lanes) = value;
     }
     else if (k == "wide4") c->wide4 = value != 0;
+    else if (k == "pt_split") c->pt_split = value != 0;
     else if (k == "use_ploc") c->use_ploc = value != 0;
     else if (k == "ploc_big") c->ploc_big = value != 0;
     else if (k == "ploc_radius") { if (value < 1 || value > 1024) { ptb_set_error("ploc_radius outside [1, 1024]"); return 1; } c->ploc_radius = value; }

@@ -170,6 +170,7 @@ struct ptb_ctx {
     cudaEvent_t lane_shade[PTB_MAX_LANES]{}, lane_shadow[PTB_MAX_LANES]{}, lane_join[PTB_MAX_LANES]{}, ev_fork = nullptr;
     cudaEvent_t ev_acc[PTB_MAX_LANES]{};   // accumulate of the last chunk of each lane (chunks add to the film in Sobol order)
     int mlt_lanes = 2;              // "mlt_lanes" / PTB_MLT_LANES: concurrent sub-populations of the MLT chains (1 = one wavefront)
+    bool pt_split = false;          // "pt_split": also split a render that fits one batch into pt_lanes concurrent chunks (measurement)
     int pt_lanes = 2;               // "pt_lanes" / PTB_PT_LANES: lanes the chunks of a multi-batch render alternate between
     bool overlap_shadow = true;     // PTB_NO_OVERLAP=1 turns the overlap off
     Ctrl* d_ctrl = nullptr;

@@ -590,10 +590,11 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
     // A render of several batches (config 4: 4 samples of a 1080p film fill the pool) runs its batches as half-sized chunks that
     // alternate between the two lanes: chunk b+1 traces while chunk b drains, each filling the SMs the other's persistent kernels leave
     // idle.  Chunks add to the film in Sobol order (the accumulate of chunk b waits for that of chunk b-1), so the film is bit-identical.
-    int nlanes = (c->pt_lanes > 1 && !c->profiling && !window && !sample_out_dev && engine != PTB_ENGINE_PREVIEW && count > per_batch) ? c->pt_lanes : 1;
+    int nlanes = (c->pt_lanes > 1 && !c->profiling && !window && !sample_out_dev && engine != PTB_ENGINE_PREVIEW && (count > per_batch || (c->pt_split && count >= c->pt_lanes))) ? c->pt_lanes : 1;
     while (nlanes > 1 && (c->max_paths / nlanes) / fm.pps < 1) nlanes--;
     const bool two = nlanes > 1;
-    const int chunk = two ? (int)((c->max_paths / nlanes) / fm.pps) : per_batch;
+    int chunk = two ? (int)((c->max_paths / nlanes) / fm.pps) : per_batch;
+    if (two && count <= per_batch) chunk = (count + nlanes - 1) / nlanes < chunk ? (count + nlanes - 1) / nlanes : chunk;      // "pt_split": one batch as nlanes concurrent chunks
     if (ensure_sobolP(c, two ? nlanes * chunk : (count < chunk ? count : chunk))) return 1;
     if (lanes_fork(c, nlanes)) return 1;
     int b = 0;
