@@ -167,20 +167,14 @@ PTB_D bool list_gate_ok(const TraceScene& S, const float4 (*s_gate)[2], int j, i
 #ifndef PTB_LIST_FILTER
 #define PTB_LIST_FILTER 1           /* 0: every entry is a candidate (A/B builds) */
 #endif
-// s_group[j] = first entry with the same inflated bounds (the two triangles of an axis-aligned wall quad share theirs): its verdict is
-// reused instead of testing the same box twice (uniform branch: every lane looks at the same j).
-PTB_D unsigned list_candidates(const int* s_slot, const int* s_group, const float4 (*s_box)[2], int nlist, int avoid_slot, const RayCons& R, const RayTrav& Q, float cull) {
-    unsigned cand = 0, pass = 0;
+PTB_D unsigned list_candidates(const int* s_slot, const float4 (*s_box)[2], int nlist, int avoid_slot, const RayCons& R, const RayTrav& Q, float cull) {
+    unsigned cand = 0;
     for (int j = 0; j < nlist; j++) {
-        const int g = s_group[j];
-        bool ok;
-        if (g == j) {
-            const float4 lo = s_box[j][0], hi = s_box[j][1];
-            float lb;
-            ok = !PTB_LIST_FILTER || (slab_trav(lo, hi, R, Q, &lb) && !(lb > cull)) || (__float_as_int(lo.w) & PTB_TF_MUST) != 0;
-            pass |= ok ? (1u << j) : 0u;
-        } else ok = (pass >> g) & 1u;
-        cand |= (ok && s_slot[j] != avoid_slot) ? (1u << j) : 0u;
+        const float4 lo = s_box[j][0], hi = s_box[j][1];
+        float lb;
+        const bool ok = !PTB_LIST_FILTER || (slab_trav(lo, hi, R, Q, &lb) && !(lb > cull));
+        const bool c = s_slot[j] != avoid_slot && (ok || (__float_as_int(lo.w) & PTB_TF_MUST) != 0);
+        cand |= c ? (1u << j) : 0u;
     }
     return cand;
 }
@@ -223,7 +217,6 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
     __shared__ float4 s_tri[PTB_LIST_CAP][4];
     __shared__ float4 s_gate[PTB_LIST_CAP][2];
     __shared__ float4 s_box[PTB_LIST_CAP][2];          // inflated bounds (lo.w: PTB_TF_* flags)
-    __shared__ int s_group[PTB_LIST_CAP];              // first entry with bit-identical bounds and flags
     const int nlist = min(S.nlist, PTB_LIST_CAP);
     for (int j = threadIdx.x; j < nlist * 4; j += 256) {
         const int slot = S.list[j >> 2];
@@ -232,16 +225,6 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
         if ((j & 3) == 2) s_box[j >> 2][0] = S.tlo[slot];
         if ((j & 3) == 3) s_box[j >> 2][1] = S.thi[slot];
         if ((j & 3) == 0) s_slot[j >> 2] = slot;
-    }
-    __syncthreads();
-    if (threadIdx.x < nlist) {
-        const int j = threadIdx.x;
-        int g = j;
-        for (int k = j - 1; k >= 0; k--) {
-            const float4 a = s_box[j][0], b = s_box[j][1], c = s_box[k][0], d = s_box[k][1];
-            if (a.x == c.x && a.y == c.y && a.z == c.z && __float_as_int(a.w) == __float_as_int(c.w) && b.x == d.x && b.y == d.y && b.z == d.z) g = k;
-        }
-        s_group[j] = g;
     }
     __syncthreads();
     const int rounded = (count + 255) & ~255;          // every thread of a block runs the same number of iterations
@@ -273,7 +256,7 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                 int jw = -1;
                 delta = trav_delta(in.ro, S.scene_abs);
                 const RayTrav Q = ray_trav(R, delta);
-                const unsigned cand = list_candidates(s_slot, s_group, s_box, nlist, in.avoid_slot, R, Q, best + best * PTB_CULL_GUARD);
+                const unsigned cand = list_candidates(s_slot, s_box, nlist, in.avoid_slot, R, Q, best + best * PTB_CULL_GUARD);
                 if (COUNT) C.boxes += nlist;
                 bool occluded = list_scan<ANYHIT, false, COUNT>(S, s_slot, s_tri, s_gate, cand, in, R, ret, best, &jw, C);
                 if (ret.hit && !list_gate_ok(S, s_gate, jw, ret.slot, R, in.ro, in.rd)) {
