@@ -56,17 +56,19 @@ struct DevCounters {
 
 // A frame covers the whole film, or -- render_tile (engine/path.py:96-118) -- one 64x64 window of it at (x0, y0); in window mode
 // every sample m of a pixel uses the SAME Sobol point with its own dimension rotation wanghash3(x, y, m) (path.py:115).
-struct FrameMap { int nx, ny, tiles_y, pps, x0, y0, window, slot_base; };   // pps = path slots per sample (multiple of 32); slot_base: first path slot of the lane
+struct FrameMap { int nx, ny, tiles_y, pps, x0, y0, window, slot_base; FastDiv d_pps, d_ty; FastMod d_dim; };   // pps = path slots per sample (multiple of 32); slot_base: first path slot of the lane
 __host__ __device__ inline FrameMap make_frame(int nx, int ny) {
     FrameMap f; f.nx = nx; f.ny = ny; f.x0 = 0; f.y0 = 0; f.window = 0; f.slot_base = 0;
     int tx = (nx + 7) / 8; f.tiles_y = (ny + 3) / 4;
     f.pps = tx * f.tiles_y * 32;
+    f.d_pps = make_fastdiv((unsigned)f.pps); f.d_ty = make_fastdiv((unsigned)f.tiles_y); f.d_dim = make_fastmod(0);      // d_dim: set by the caller that knows the Sobol table
     return f;
 }
 __host__ __device__ inline FrameMap make_window(int nx, int ny, int x0, int y0, int w, int h) {
     FrameMap f; f.nx = nx; f.ny = ny; f.x0 = x0; f.y0 = y0; f.window = 1; f.slot_base = 0;
     int tx = (w + 7) / 8; f.tiles_y = (h + 3) / 4;
     f.pps = tx * f.tiles_y * 32;
+    f.d_pps = make_fastdiv((unsigned)f.pps); f.d_ty = make_fastdiv((unsigned)f.tiles_y); f.d_dim = make_fastmod(0);      // d_dim: set by the caller that knows the Sobol table
     return f;
 }
 

@@ -54,6 +54,37 @@ PTB_HD float lerpf(float f, float a, float b) { return a * (1.0f - f) + b * f; }
 PTB_HD V3 lerp3(float f, V3 a, V3 b) { return a * (1.0f - f) + b * f; }
 PTB_HD int pymod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
+// ---- exact integer division / modulo by a divisor fixed per launch (a runtime `/` or `%` is ~25-35 instructions; these are 2-10) ----
+// FastDiv: floor(n / d) for 0 <= n < 2^31.  d a power of two: a shift.  Otherwise, with L = ceil(log2 d) and M = floor(2^(31+L) / d) + 1
+// (fits 32 bits), M*d = 2^(31+L) + e with 0 < e <= d, so n*M / 2^(31+L) = n/d + n*e / (d * 2^(31+L)) and the excess is below 2^-L < 1/d:
+// it never reaches the next integer.  tests/test_fastdiv_cpu.py checks both against Python's // and % on boundary and random inputs.
+struct FastDiv { unsigned d, M; int sh; };
+inline __host__ __device__ FastDiv make_fastdiv(unsigned d) {
+    FastDiv f; f.d = d; f.M = 0; f.sh = 0;
+    int L = 0; while ((1ull << L) < d) L++;
+    if ((d & (d - 1)) == 0) f.sh = L;
+    else { f.M = (unsigned)(((1ull << (31 + L)) / d) + 1ull); f.sh = L - 1; }
+    return f;
+}
+PTB_D unsigned fastdiv(unsigned n, const FastDiv& f) { return f.M ? (__umulhi(n, f.M) >> f.sh) : (n >> f.sh); }
+// FastMod: Python-style i mod m for ANY int32 i (the Sobol dimension rotation wraps through the whole i32 range, sobol.py:107-125).
+// q = floor(n / m) for the unsigned n = i mod 2^32 via M = floor(2^64 / m) + 1 (excess below 2^-32 < 1/m); a negative i is n - 2^32, so
+// its residue is (n mod m) - (2^32 mod m), brought back into [0, m).
+struct FastMod { unsigned m, K; unsigned long long M; };
+inline __host__ __device__ FastMod make_fastmod(unsigned m) {
+    FastMod f; f.m = m; f.K = 0; f.M = 0;
+    if (m > 1) { f.M = 0xFFFFFFFFFFFFFFFFull / m + 1ull; f.K = (unsigned)((1ull << 32) % m); }      // m == 1: M stays 0 and every residue is 0
+    return f;
+}
+PTB_D int fastpymod(int i, const FastMod& f) {
+    if (f.M == 0ull) return 0;
+    const unsigned n = (unsigned)i;
+    const unsigned q = (unsigned)__umul64hi((unsigned long long)n, f.M);
+    int r = (int)(n - q * f.m);
+    if (i < 0) { r -= (int)f.K; if (r < 0) r += (int)f.m; }
+    return r;
+}
+
 // int(ti.floor(x)): NaN / out-of-range -> INT_MIN (x86 cvttss2si), which every call site then clamps
 PTB_D int ifloor(float x) {
     float f = floorf(x);

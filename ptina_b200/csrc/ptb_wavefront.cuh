@@ -6,7 +6,7 @@
 // ---- pixel <-> path-slot mapping: a warp owns an 8x4 pixel tile so primary rays stay coherent (FrameMap: ptb_internal.h) -----
 PTB_D bool slot_pixel(const FrameMap& f, int q, int* x, int* y) {
     int tile = q >> 5, lane = q & 31;
-    int tx = tile / f.tiles_y, ty = tile - tx * f.tiles_y;
+    int tx = (int)fastdiv((unsigned)tile, f.d_ty), ty = tile - tx * f.tiles_y;
     *x = f.x0 + tx * 8 + (lane >> 2);
     *y = f.y0 + ty * 4 + (lane & 3);
     return *x < f.nx && *y < f.ny;
@@ -20,14 +20,15 @@ PTB_D void frame_rng(const FrameMap& f, const float* __restrict__ tab, int dim, 
 struct Rng {
     const float* __restrict__ tab;
     int base, dim;   // dim == 0 -> direct indexing (MLT)
+    FastMod fmod;    // i mod dim without a runtime division
     PTB_D float draw(int c) const {
         if (dim == 0) return tab[c];
         int i = (int)((unsigned)base + (unsigned)c);   // i32 wrap of `self.i += 1`
-        return __ldg(&tab[pymod(i, dim)]);
+        return __ldg(&tab[fastpymod(i, fmod)]);
     }
 };
 PTB_D void frame_rng(const FrameMap& f, const float* __restrict__ tab, int dim, int s, int x, int y, Rng* rng) {
-    rng->dim = dim;
+    rng->dim = dim; rng->fmod = f.d_dim;
     if (f.window) { rng->tab = tab; rng->base = wanghash(s ^ wanghash2(x, y)); }
     else { rng->tab = tab + (size_t)s * dim; rng->base = wanghash2(x, y); }
 }
@@ -39,14 +40,14 @@ struct RngRun {
         if (g.dim != 0) {
             i0 = (int)((unsigned)g.base + (unsigned)c0);
             fast = i0 <= 0x7fffffff - 16;
-            b0 = pymod(i0, g.dim);
+            b0 = fastpymod(i0, g.fmod);
         } else i0 = c0;
     }
     PTB_D float draw(int j) const {     // j-th draw of the run, j < 16
         if (g.dim == 0) return g.tab[i0 + j];
         int b;
         if (fast) { b = b0 + j; if (b >= g.dim) b -= g.dim; }
-        else b = pymod((int)((unsigned)i0 + (unsigned)j), g.dim);
+        else b = fastpymod((int)((unsigned)i0 + (unsigned)j), g.fmod);
         return __ldg(&g.tab[b]);
     }
 };

@@ -64,10 +64,10 @@ __global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* 
             int hit_index = __float_as_int(h4.w);
             bool hit = hit_index >= 0;
             Rng rng;
-            if (dim == 0) { rng.tab = rngtab + (size_t)p * rng_stride; rng.base = 0; rng.dim = 0; }
+            if (dim == 0) { rng.tab = rngtab + (size_t)p * rng_stride; rng.base = 0; rng.dim = 0; rng.fmod = fm.d_dim; }
             else {
                 const int lp = p - fm.slot_base;                      // slot within the lane's share of the pool
-                int s = lp / fm.pps, q = lp - s * fm.pps, x, y;
+                int s = (int)fastdiv((unsigned)lp, fm.d_pps), q = lp - s * fm.pps, x, y;
                 slot_pixel(fm, q, &x, &y);
                 frame_rng(fm, rngtab, dim, s, x, y, &rng);
             }

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BLK) k_raygen(const SceneParams* __restrict__ 
         bool live = false;
         V3 ro = v3s(0.0f), rd = v3s(0.0f);
         if (p < total) {
-            int s = p / fm.pps, q = p - s * fm.pps;
+            int s = (int)fastdiv((unsigned)p, fm.d_pps), q = p - s * fm.pps;
             int x, y;
             if (slot_pixel(fm, q, &x, &y)) {
                 live = true;
@@ -551,6 +551,7 @@ int ptb_wf_render(ptb_ctx* c, int engine, int k_first, int count, int stride, fl
     cudaStream_t st = c->stream;
     DevCounters* ctr = c->counting ? c->d_counters : nullptr;
     FrameMap fm = window ? make_window(c->nx, c->ny, window[0], window[1], window[2], window[3]) : make_frame(c->nx, c->ny);
+    fm.d_dim = make_fastmod((unsigned)c->sobol_dim);
 
     if (engine == PTB_ENGINE_MLT) {
         if (c->mlt_count <= 0) { ptb_set_error("MLT chains not initialised (ptb_mlt_reset)"); return 1; }
@@ -645,6 +646,7 @@ int ptb_wf_trace_primary(ptb_ctx* c, int k, float* rays_dev, int32_t* hit_dev, f
     if (ptb_wf_upload_params(c)) return 1;
     cudaStream_t st = c->stream;
     FrameMap fm = make_frame(c->nx, c->ny);
+    fm.d_dim = make_fastmod((unsigned)c->sobol_dim);
     if (fm.pps > c->max_paths) { ptb_set_error("film larger than the path pool"); return 1; }
     if (ensure_sobolP(c, 1)) return 1;
     if (ptb_wf_sobol_points(c, k, 1, 1, c->d_sobolP)) return 1;
