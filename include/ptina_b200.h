@@ -185,6 +185,10 @@ int ptb_occluded(ptb_ctx* ctx, const float* rays, const int32_t* avoid, const fl
  * eval -> out [m][3];  sample -> out [m][7] = outdir, pdf, color */
 int ptb_eval_bsdf(ptb_ctx* ctx, const float* params, const float* geom, int m, float* out);
 int ptb_sample_bsdf(ptb_ctx* ctx, const float* params, const float* geom, int m, float* out);
+/* the same two with every term of disney.py evaluated as written -- the production forms above leave out factors that an exactly-zero
+ * material weight (transmission, clearcoat, subsurface) annihilates; the tests compare the two bit for bit */
+int ptb_eval_bsdf_literal(ptb_ctx* ctx, const float* params, const float* geom, int m, float* out);
+int ptb_sample_bsdf_literal(ptb_ctx* ctx, const float* params, const float* geom, int m, float* out);
 int ptb_material_get(ptb_ctx* ctx, const int32_t* mtlid, const float* uv, int m, float* out14);   /* mtllib.py:79-95 */
 int ptb_light_hit(ptb_ctx* ctx, const float* rays, int m, float* out6);                            /* light/__init__.py:51-81 */
 int ptb_light_sample(ptb_ctx* ctx, const float* hitpos_samp, int m, float* out8);                  /* light/__init__.py:83-121 */

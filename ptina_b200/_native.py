@@ -49,7 +49,7 @@ SYMBOLS = [
     'ptb_set_camera', 'ptb_build_tree', 'ptb_set_traversal', 'ptb_export_tree', 'ptb_export_traversal', 'ptb_set_size', 'ptb_get_size', 'ptb_clear',
     'ptb_film_ptr', 'ptb_render', 'ptb_render_tile', 'ptb_render_final', 'ptb_render_range', 'ptb_mlt_reset', 'ptb_mlt_set_param', 'ptb_mlt_state', 'ptb_get_image',
     'ptb_fast_export_image', 'ptb_fast_export_gl', 'ptb_get_film', 'ptb_trace_primary', 'ptb_intersect', 'ptb_occluded', 'ptb_eval_bsdf',
-    'ptb_sample_bsdf', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_normaldist', 'ptb_render_sample',
+    'ptb_sample_bsdf', 'ptb_eval_bsdf_literal', 'ptb_sample_bsdf_literal', 'ptb_material_get', 'ptb_light_hit', 'ptb_light_sample', 'ptb_world_at', 'ptb_normaldist', 'ptb_render_sample',
     'ptb_set_counting', 'ptb_get_counters', 'ptb_reset_counters', 'ptb_get_stage_ms', 'ptb_get_launches', 'ptb_measure_l2', 'ptb_selftest',
 ]
 
@@ -392,6 +392,12 @@ class Context:
 
     def sample_bsdf(self, params, geom):
         return self._tap(self.L.ptb_sample_bsdf, params, 14, geom, 10, 7)
+
+    def eval_bsdf_literal(self, params, geom):
+        return self._tap(self.L.ptb_eval_bsdf_literal, params, 14, geom, 10, 3)
+
+    def sample_bsdf_literal(self, params, geom):
+        return self._tap(self.L.ptb_sample_bsdf_literal, params, 14, geom, 10, 7)
 
     def material_get(self, mtlid, uv):
         return self._tap(self.L.ptb_material_get, uv, 2, None, 0, 14, ints=mtlid)

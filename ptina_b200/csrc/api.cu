@@ -594,6 +594,8 @@ static int shade_tap(ptb_ctx* c, int what, const float* in0, size_t n0, const fl
 }
 int ptb_eval_bsdf(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 0, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 3); }
 int ptb_sample_bsdf(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 1, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 7); }
+int ptb_eval_bsdf_literal(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 6, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 3); }
+int ptb_sample_bsdf_literal(ptb_ctx* c, const float* params, const float* geom, int m, float* out) { return shade_tap(c, 7, params, (size_t)m * 14, geom, (size_t)m * 10, nullptr, m, out, (size_t)m * 7); }
 int ptb_material_get(ptb_ctx* c, const int32_t* mtlid, const float* uv, int m, float* out) { return shade_tap(c, 2, uv, (size_t)m * 2, nullptr, 0, mtlid, m, out, (size_t)m * 14); }
 int ptb_light_hit(ptb_ctx* c, const float* rays, int m, float* out) { return shade_tap(c, 3, rays, (size_t)m * 6, nullptr, 0, nullptr, m, out, (size_t)m * 6); }
 int ptb_light_sample(ptb_ctx* c, const float* in, int m, float* out) { return shade_tap(c, 4, in, (size_t)m * 6, nullptr, 0, nullptr, m, out, (size_t)m * 8); }

@@ -32,6 +32,7 @@ struct Disney {            // materials/disney.py:14-50
     V3 basecolor; float metallic, roughness, specular, specularTint, subsurface, sheen, sheenTint, clearcoat,
         clearcoatGloss, transmission, ior;
     V3 speccolor, sheencolor; float alpha, clearcoatAlpha;
+    int elim;              // PTB_ELIM_* : terms of brdf / bounce that are exactly zero for this material and may be left out (disney_init)
 };
 struct BSDFSample { V3 outdir; float pdf; V3 color; };   // materials/__init__.py:8-18
 
@@ -64,6 +65,35 @@ PTB_D V4 param_get(const SceneParams* P, const float4* __restrict__ texels, int 
     return fac;
 }
 
+// ---- terms that vanish exactly ----------------------------------------------------------------------------------
+// Disney.brdf / Disney.bounce (disney.py:52-233) always evaluate every lobe and multiply by the material's weights.  When a weight is
+// EXACTLY zero -- transmission, clearcoat, subsurface of every material of configs 1, 2 and 4 -- the product is +-0 provided the other
+// factor is finite, and adding +-0 leaves the sum as it is (bit for bit, but for the sign of a zero result, which nothing downstream can
+// see: the value is only added, multiplied or compared).  So the factor need not be computed: the transmission Fresnel term (two
+// square roots, three divisions), the clearcoat lobe (a logarithm, two square roots, three divisions) and the subsurface term (a
+// division) are 250 of the ~1340 instructions of a path vertex.  Finiteness is not assumed but guarded: a material qualifies only if
+// every parameter is finite and of ordinary size (`sane`: |x| <= 1e4, ior >= 1e-3, so that both refraction indices are positive), and
+// each call site adds the cheap run-time condition under which the skipped factor is provably finite (stated there); when a guard fails
+// the literal expression runs, so non-finite values (NaN from 0 * inf) come out exactly where the reference produces them.
+// disney_brdf_t<false> / disney_bounce_t<false> are the literal evaluations; tests/test_gpu_parity.py compares the two bit for bit.
+#define PTB_ELIM_TRANS 1          /* transmission == 0 */
+#define PTB_ELIM_COAT 2           /* clearcoat == 0 and clearcoatAlpha in [1e-3, 0.5] */
+#define PTB_ELIM_SS 4             /* subsurface == 0 */
+#ifndef PTB_DEAD_TERMS
+#define PTB_DEAD_TERMS 1          /* 0: always the literal expressions (A/B builds) */
+#endif
+PTB_D int disney_elim(const Disney& m) {
+    const float B = 1e4f;
+    bool sane = fabsf(m.basecolor.x) <= B && fabsf(m.basecolor.y) <= B && fabsf(m.basecolor.z) <= B && fabsf(m.metallic) <= B && fabsf(m.roughness) <= B &&
+                fabsf(m.specular) <= B && fabsf(m.specularTint) <= B && fabsf(m.subsurface) <= B && fabsf(m.sheen) <= B && fabsf(m.sheenTint) <= B &&
+                fabsf(m.clearcoat) <= B && fabsf(m.clearcoatGloss) <= B && fabsf(m.transmission) <= B && m.ior >= 1e-3f && m.ior <= B;      // NaNs fail
+    sane = sane && fabsf(m.sheencolor.x) <= B && fabsf(m.sheencolor.y) <= B && fabsf(m.sheencolor.z) <= B;
+    int e = 0;
+    if (sane && m.transmission == 0.0f) e |= PTB_ELIM_TRANS;
+    if (sane && m.clearcoat == 0.0f && m.clearcoatAlpha >= 1e-3f && m.clearcoatAlpha <= 0.5f) e |= PTB_ELIM_COAT;
+    if (sane && m.subsurface == 0.0f) e |= PTB_ELIM_SS;
+    return e;
+}
 // ---- materials/disney.py:14-50 --------------------------------------------------------------------------
 PTB_D void disney_init(Disney& m) {
     V3 tint = v3s(1.0f);
@@ -73,6 +103,7 @@ PTB_D void disney_init(Disney& m) {
     m.sheencolor = lerp3(m.sheenTint, v3s(1.0f), tint);
     m.alpha = fmaxf(0.001f, m.roughness * m.roughness);
     m.clearcoatAlpha = lerpf(m.clearcoatGloss, 0.1f, 0.001f);
+    m.elim = disney_elim(m);
 }
 // ---- mtllib.py:79-95 MaterialPool.get ---------------------------------------------------------------------
 PTB_D Disney material_get(const SceneParams* P, const float4* __restrict__ texels, int mtlid, float u, float v) {
@@ -137,8 +168,8 @@ PTB_D V3 sample_GTR2(float u, float v, float alpha) {   // microfacet.py:74-77
     return spherical(u, v);
 }
 
-// ---- materials/disney.py:52-106 Disney.brdf (value excludes the cosine) --------------------------------------
-PTB_D V3 disney_brdf(const Disney& m, V3 normal, float sign, V3 indir, V3 outdir) {
+// ---- materials/disney.py:52-106 Disney.brdf (value excludes the cosine), every term as written --------------------------------------
+PTB_D V3 disney_brdf_literal(const Disney& m, V3 normal, float sign, V3 indir, V3 outdir) {
     float etai = 1.0f, etao = m.ior;
     if (sign < 0.0f) { etai = m.ior; etao = 1.0f; }
     V3 halfdir = normalized(indir + outdir);
@@ -185,10 +216,16 @@ struct Choice {
         if (w < r) { w /= r; pdf *= r; return 1; }
         w = (w - r) / (1.0f - r); pdf *= 1.0f - r; return 0;
     }
+    // the same; a rate of exactly zero (no clearcoat, no transmission) is decided without the division: for w >= 0 or NaN the test
+    // w < 0 fails, (w - 0) / (1 - 0) = w and pdf * 1 = pdf
+    PTB_D int pick_z(float r) {
+        if (r == 0.0f && !(w < 0.0f)) return 0;
+        return pick(r);
+    }
 };
 
-// ---- materials/disney.py:114-233 Disney.bounce ------------------------------------------------------------------
-PTB_D BSDFSample disney_bounce(const Disney& m, V3 normal, float sign, V3 indir, V3 samp) {
+// ---- materials/disney.py:114-233 Disney.bounce, as written ------------------------------------------------------------------
+PTB_D BSDFSample disney_bounce_literal(const Disney& m, V3 normal, float sign, V3 indir, V3 samp) {
     BSDFSample res; res.outdir = v3s(0.0f); res.pdf = 0.0f; res.color = v3s(0.0f);
     float etai = 1.0f, etao = m.ior;
     if (sign < 0.0f) { etai = m.ior; etao = 1.0f; }
@@ -264,6 +301,178 @@ PTB_D BSDFSample disney_bounce(const Disney& m, V3 normal, float sign, V3 indir,
         res.color = diffuse * PTB_PI * (1.0f - m.metallic) * (1.0f - m.transmission) / choice.pdf;
     }
     return res;
+}
+
+
+// ---- the production forms: the same values (see "terms that vanish exactly" above) -----------------------------------------------
+// magnitudes under which the skipped factors below are provably finite; directions are unit vectors in the renderer (the taps may pass anything)
+PTB_D bool elim_dirs_ok(float cosi, float coso, float cosoh) { return fabsf(cosi) <= 4.0f && fabsf(coso) <= 4.0f && cosoh <= 4.0f; }
+PTB_D V3 disney_brdf(const Disney& m, V3 normal, float sign, V3 indir, V3 outdir) {
+#if !PTB_DEAD_TERMS
+    return disney_brdf_literal(m, normal, sign, indir, outdir);
+#else
+    const int el = m.elim;
+    float etai = 1.0f, etao = m.ior;
+    if (sign < 0.0f) { etai = m.ior; etao = 1.0f; }
+    V3 halfdir = normalized(indir + outdir);
+    float cosi = dot(indir, normal), coso = dot(outdir, normal);
+    float cosh = dot_or_zero(halfdir, normal), cosoh = dot_or_zero(halfdir, outdir);
+    const bool dirs_ok = elim_dirs_ok(cosi, coso, cosoh);
+    V3 result = v3s(0.0f);
+    if (coso < 0.0f) {
+        if (cosi >= 0.0f) {
+            // transmission == 0: the value is (finite) * 0.  Finite: cosh <= 0.99999 keeps GTR2's t = 1 + (a2-1) cosh^2 >= 2e-5 (a2 <= 1e16),
+            // dielectricFresnel is in [0, 1] for positive finite indices, basecolor and metallic are bounded by `sane`.
+            if (!((el & PTB_ELIM_TRANS) && dirs_ok && cosh <= 0.99999f)) {
+                float Ds = GTR2(cosh, m.alpha);
+                float fdf = dielectricFresnel(etao, etai, cosoh);
+                V3 transmit = (1.0f / PTB_PI) * m.basecolor * (1.0f - fdf) * Ds;
+                result = transmit * (1.0f - m.metallic) * m.transmission;
+            }
+        }
+    } else {
+        float Fi = schlickFresnel(cosi), Fo = schlickFresnel(coso);
+        float Fd90 = 0.5f + 2.0f * (cosoh * cosoh) * m.roughness;
+        float Fd = lerpf(Fi, 1.0f, Fd90) * lerpf(Fo, 1.0f, Fd90);
+        float Foh = schlickFresnel(cosoh);
+        V3 Fsheen = (Foh * m.sheen) * m.sheencolor;
+        float Ds = GTR2(cosh, m.alpha);
+        V3 Fs = lerp3(Foh, m.speccolor, v3s(1.0f));
+        float Gs = smithGGX(cosi, m.alpha) * smithGGX(coso, m.alpha);
+        // subsurface == 0: lerp(0, Fd, ss) = Fd * 1 + ss * 0 = Fd for finite ss; |cosi + coso| > 1e-20 bounds its 1 / (cosi + coso)
+        float dl;
+        if ((el & PTB_ELIM_SS) && dirs_ok && fabsf(cosi + coso) > 1e-20f) dl = Fd;
+        else {
+            float Fss90 = (cosoh * cosoh) * m.roughness;
+            float Fss = lerpf(Fi, 1.0f, Fss90) * lerpf(Fo, 1.0f, Fss90);
+            float ss = 1.25f * (Fss * (1.0f / (cosi + coso) - 0.5f) + 0.5f);
+            dl = lerpf(m.subsurface, Fd, ss);
+        }
+        V3 diffuse = ((1.0f / PTB_PI) * dl) * m.basecolor + Fsheen;
+        // clearcoat == 0: 0.25 * 0 * Gr * Fr * Dr.  Gr <= 16 for cosines in [0, 4] (smithGGX(c, 0.25) <= 4), Fr in [0.04, 1], and
+        // GTR1's t >= 2e-5 for cosh <= 0.99999 with a2 = clearcoatAlpha^2 in [1e-6, 0.25] (log a2 in [-13.9, -1.38])
+        V3 specular = (Gs * Fs) * Ds;
+        if (!((el & PTB_ELIM_COAT) && dirs_ok && cosi >= 0.0f && cosh <= 0.99999f)) {
+            float Dr = GTR1(cosh, m.clearcoatAlpha);
+            float Gr = smithGGX(cosi, 0.25f) * smithGGX(coso, 0.25f);
+            float Fr = lerpf(Foh, 0.04f, 1.0f);
+            specular = specular + v3s(0.25f * m.clearcoat * Gr * Fr * Dr);
+        }
+        result = diffuse * (1.0f - m.metallic) * (1.0f - m.transmission);
+        // transmission == 0: transmit * (1 - metallic) * 0 with transmit = (1/pi) fdf Ds basecolor finite for |Ds| <= 1e30
+        if (!((el & PTB_ELIM_TRANS) && dirs_ok && fabsf(Ds) <= 1e30f)) {
+            float fdf = dielectricFresnel(etao, etai, cosoh);
+            V3 transmit = ((1.0f / PTB_PI) * fdf * Ds) * m.basecolor;
+            result = result + transmit * (1.0f - m.metallic) * m.transmission;
+        }
+        result = result + specular * (1.0f - m.transmission);
+    }
+    return result;
+#endif
+}
+
+// Disney.bounce.  Besides the vanishing terms: (i) the three lobes all end in `tanspace(normal) @ spherical(h, samp.y)` -- a square
+// root, a division, a sincos and two cross products -- with only h depending on the lobe; a warp whose lanes picked different lobes
+// used to run that tail once per lobe, now h is chosen inside the branch and the tail runs once for all lanes (same operations on
+// the same operands: same bits); (ii) eta = etai / etao is only read by refract(), so the division moves into that branch.
+PTB_D BSDFSample disney_bounce(const Disney& m, V3 normal, float sign, V3 indir, V3 samp) {
+#if !PTB_DEAD_TERMS
+    return disney_bounce_literal(m, normal, sign, indir, samp);
+#else
+    const int el = m.elim;
+    BSDFSample res; res.outdir = v3s(0.0f); res.pdf = 0.0f; res.color = v3s(0.0f);
+    float etai = 1.0f, etao = m.ior;
+    if (sign < 0.0f) { etai = m.ior; etao = 1.0f; }
+    float Fi = schlickFresnel(dot(indir, normal));
+    V3 Fs = lerp3(Fi, m.speccolor, v3s(1.0f));
+    Choice choice; choice.pdf = 1.0f; choice.w = samp.z;
+    float specrate = lerpf(m.transmission, lerpf(m.metallic, vavg(Fs), 1.0f), 1.0f);
+    float coatrate = 0.04f * m.clearcoat;
+    specrate = lerpf(specrate, 0.1f, 1.0f);
+    if (coatrate != 0.0f) coatrate = lerpf(coatrate, 0.1f, 1.0f);
+
+    int lobe; float h;
+    if (choice.pick_z(coatrate)) {
+        lobe = 0;
+        const float alpha = m.clearcoatAlpha;
+        h = sqrtf(powf(alpha, 2.0f - 2.0f * samp.x) - 1.0f) / (alpha * alpha - 1.0f);       // sample_GTR1
+    } else if (choice.pick_z(specrate)) {
+        lobe = 1;
+        h = sqrtf((1.0f - samp.x) / (1.0f - samp.x * (1.0f - m.alpha * m.alpha)));           // sample_GTR2
+    } else {
+        lobe = 2;
+        h = sqrtf(samp.x);
+    }
+    const V3 dirv = matvec(tanspace(normal), spherical(h, samp.y));
+    if (lobe == 0) {
+        float alpha = m.clearcoatAlpha;
+        V3 halfdir = dirv;
+        V3 outdir = reflect(-indir, halfdir);
+        float coso = dot(outdir, normal);
+        float cosh = dot_or_zero(halfdir, normal), cosoh = dot_or_zero(halfdir, outdir);
+        if (cosoh > 0.0f) {
+            float Dr = GTR1(cosh, alpha);
+            float Fr = lerpf(schlickFresnel(cosoh), 0.04f, 1.0f);
+            res.outdir = outdir;
+            float partial = m.clearcoat * Fr * coso / cosoh;
+            res.pdf = Dr * partial;
+            res.color = v3s(partial / choice.pdf);
+        }
+    } else if (lobe == 1) {
+        float alpha = m.alpha;
+        V3 halfdir = dirv;
+        V3 outdir = reflect(-indir, halfdir);
+        float coso = dot_or_zero(outdir, normal);
+        float cosh = dot_or_zero(halfdir, normal), cosoh = dot_or_zero(halfdir, outdir);
+        if (cosoh > 0.0f && coso > 0.0f && cosh > 0.0f) {
+            float Ds = GTR2(cosh, alpha);
+            if (choice.pick_z(m.transmission)) {
+                float fdf = dielectricFresnel(etao, etai, cosoh);
+                float reflrate = lerpf(fdf, 0.2f, 1.0f);
+                if (choice.pick(reflrate)) {
+                    res.outdir = outdir;
+                    res.pdf = Ds * fdf;
+                    res.color = m.basecolor * fdf * m.transmission / choice.pdf;
+                } else {
+                    V3 T;
+                    if (refract(-indir, halfdir, etai / etao, &T)) {
+                        res.outdir = T;
+                        res.pdf = Ds * (1.0f - fdf);
+                        res.color = m.basecolor * (1.0f - fdf) * m.transmission / choice.pdf;
+                    }
+                }
+            } else {
+                V3 Fs2 = lerp3(schlickFresnel(cosoh), m.speccolor, v3s(1.0f));
+                res.outdir = outdir;
+                float partial = 0.5f / (cosoh * smithGGX(coso, alpha));
+                res.pdf = Ds * vavg(Fs2) * partial;
+                res.color = Fs2 * partial * (1.0f - m.transmission) / choice.pdf;
+            }
+        }
+    } else {
+        V3 outdir = dirv;
+        V3 halfdir = normalized(indir + outdir);
+        float cosi = dot(indir, normal), coso = dot(outdir, normal);
+        float cosoh = dot_or_zero(halfdir, outdir);
+        float Fi2 = schlickFresnel(cosi), Fo = schlickFresnel(coso);
+        float Fd90 = 0.5f + 2.0f * (cosoh * cosoh) * m.roughness;
+        float Fd = lerpf(Fi2, 1.0f, Fd90) * lerpf(Fo, 1.0f, Fd90);
+        float dl;
+        if ((el & PTB_ELIM_SS) && elim_dirs_ok(cosi, coso, cosoh) && fabsf(cosi + coso) > 1e-20f) dl = Fd;       // as in disney_brdf
+        else {
+            float Fss90 = (cosoh * cosoh) * m.roughness;
+            float Fss = lerpf(Fi2, 1.0f, Fss90) * lerpf(Fo, 1.0f, Fss90);
+            float ss = 1.25f * (Fss * (1.0f / (cosi + coso) - 0.5f) + 0.5f);
+            dl = lerpf(m.subsurface, Fd, ss);
+        }
+        V3 Fsheen = (schlickFresnel(cosoh) * m.sheen) * m.sheencolor;
+        V3 diffuse = ((1.0f / PTB_PI) * dl) * m.basecolor + Fsheen;
+        res.outdir = outdir;
+        res.pdf = 1.0f / PTB_PI;
+        res.color = diffuse * PTB_PI * (1.0f - m.metallic) * (1.0f - m.transmission) / choice.pdf;
+    }
+    return res;
+#endif
 }
 
 // engine/path.py:10-14

@@ -155,20 +155,20 @@ PTB_D Disney disney_from(const float* p) {
     disney_init(m);
     return m;
 }
-// what: 0 eval_bsdf, 1 sample_bsdf, 2 material_get, 3 light_hit, 4 light_sample, 5 world_at
+// what: 0 eval_bsdf, 1 sample_bsdf, 2 material_get, 3 light_hit, 4 light_sample, 5 world_at, 6 / 7 eval / sample with every term as written (checkers)
 __global__ void __launch_bounds__(BLK) k_shade_tap(const SceneParams* __restrict__ P, const float4* __restrict__ texels, int what, const float* __restrict__ in0,
                                                    const float* __restrict__ in1, const int* __restrict__ ini, int m, float* __restrict__ out) {
     int i = blockIdx.x * BLK + threadIdx.x;
     if (i >= m) return;
-    if (what == 0 || what == 1) {
+    if (what == 0 || what == 1 || what == 6 || what == 7) {
         Disney d = disney_from(in0 + 14 * i);
         const float* g = in1 + 10 * i;
         V3 nrm = mk3(g[0], g[1], g[2]), wi = mk3(g[4], g[5], g[6]), x = mk3(g[7], g[8], g[9]);
-        if (what == 0) {
-            V3 r = disney_brdf(d, nrm, g[3], wi, x);
+        if (what == 0 || what == 6) {
+            V3 r = what == 0 ? disney_brdf(d, nrm, g[3], wi, x) : disney_brdf_literal(d, nrm, g[3], wi, x);
             out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
         } else {
-            BSDFSample s = disney_bounce(d, nrm, g[3], wi, x);
+            BSDFSample s = what == 1 ? disney_bounce(d, nrm, g[3], wi, x) : disney_bounce_literal(d, nrm, g[3], wi, x);
             float* o = out + 7 * i;
             o[0] = s.outdir.x; o[1] = s.outdir.y; o[2] = s.outdir.z; o[3] = s.pdf; o[4] = s.color.x; o[5] = s.color.y; o[6] = s.color.z;
         }

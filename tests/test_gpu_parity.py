@@ -450,6 +450,66 @@ def test_bsdf_sample_within_1e5(gpu):
     assert (b[:, 3] == 0).any() and np.isclose(b[:, 3], 1 / np.pi).any() and (params[:, 12] > 0).any()
 
 
+def _adversarial_bsdf_inputs(rng, m):
+    """Materials with exact zeros / odd values and direction sets built to hit the guards of the production BSDF forms."""
+    params = _random_materials(rng, m)
+    k = m // 8
+    params[:k, 12] = 0.0; params[:k, 10] = 0.0; params[:k, 7] = 0.0                       # the config 1 / 2 / 4 kind: everything eliminable
+    params[k:2 * k, 12] = -0.0; params[k:2 * k, 10] = -0.0                                   # negative zeros
+    odd = slice(2 * k, 3 * k)
+    params[odd, 13] = rng.choice([0.0, 1e-4, 1.0, 1e5, np.inf, np.nan], k)                  # ior outside the `sane` range
+    params[odd, 4] = rng.choice([0.0, 1e-3, 1.0, 50.0, 2e4], k)                              # roughness
+    params[odd, 11] = rng.choice([0.0, 1.0, 1.0101, 2.0, -5.0, 1e6], k)                      # clearcoatGloss: clearcoatAlpha 0 / negative / 1
+    params[odd, 0] = rng.choice([0.0, 1.0, 1e5, np.nan], k)
+    params[odd, 12] = 0.0; params[odd, 10] = 0.0; params[odd, 7] = 0.0
+    nrm = _unit(rng, m)
+    wi, wo = _unit(rng, m), _unit(rng, m)
+    sign = np.ones((m, 1), np.float32)
+    j = np.arange(m)
+    wo[j % 7 == 0] = -wi[j % 7 == 0]                                                         # half vector 0 / 0
+    r = j % 7 == 1                                                                           # mirror direction: half vector == normal (cosh = 1)
+    wo[r] = 2 * (wi[r] * nrm[r]).sum(1, keepdims=True) * nrm[r] - wi[r]
+    wo[j % 7 == 2] *= np.float32(1e3)                                                        # not unit: the magnitude guards
+    wi[j % 7 == 3] *= np.float32(1e20)
+    g = j % 7 == 4                                                                           # grazing: cosi + coso ~ 0
+    t = np.cross(nrm[g], _unit(rng, int(g.sum())))
+    t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-20)
+    wi[g] = t.astype(np.float32); wo[g] = -t.astype(np.float32) + np.float32(1e-7) * nrm[g]
+    sign[j % 5 == 0] = -1.0                                                                  # the taps accept it; the integrator never passes it
+    return params, nrm, sign, wi, wo
+
+
+def test_bsdf_production_forms_equal_the_literal_ones_bitwise(gpu):
+    # ptb_shade.cuh "terms that vanish exactly": the production disney_brdf / disney_bounce leave out factors an exactly-zero weight
+    # annihilates (under guards that make the skipped factor finite) and share the tail of the three lobes; the literal forms evaluate
+    # disney.py:52-233 term by term.  Same bits (a zero may differ in sign), NaNs in the same places.
+    rng = np.random.default_rng(2026)
+    m = 280000
+    params, nrm, sign, wi, wo = _adversarial_bsdf_inputs(rng, m)
+    geom = np.concatenate([nrm, sign, wi, wo], 1).astype(np.float32)
+    with np.errstate(all='ignore'):
+        a, b = gpu.eval_bsdf(params, geom), gpu.eval_bsdf_literal(params, geom)
+        assert np.array_equal(a, b, equal_nan=True), int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum())
+        assert np.isnan(b).any() and np.isinf(b).any() and (b == 0).any()                    # the fall-backs were exercised
+        samp = rng.random((m, 3)).astype(np.float32)
+        samp[::11, 2] = 0.0; samp[1::11, 2] = -0.25; samp[2::11, 0] = 1.0; samp[3::11, 0] = 0.0; samp[4::11, 2] = np.nan
+        geom = np.concatenate([nrm, sign, wi, samp], 1).astype(np.float32)
+        a, b = gpu.sample_bsdf(params, geom), gpu.sample_bsdf_literal(params, geom)
+        assert np.array_equal(a, b, equal_nan=True), int((~((a == b) | (np.isnan(a) & np.isnan(b)))).sum())
+        lobes = (np.isclose(b[:, 3], 1 / np.pi).any(), (b[:, 3] == 0).any(), ((b[:, :3] * nrm).sum(1) < -0.1).any())
+        assert all(lobes), lobes
+    # and the plain production call on the renderer's own kind of input (eliminable material, unit directions, facing normal)
+    n2 = 100000
+    p2 = _random_materials(rng, n2); p2[:, 12] = 0.0; p2[:, 10] = 0.0; p2[:, 7] = 0.0
+    nr, w1, w2 = _unit(rng, n2), _unit(rng, n2), _unit(rng, n2)
+    flip = (w1 * nr).sum(1) < 0
+    w1[flip] = -w1[flip]
+    g2 = np.concatenate([nr, np.ones((n2, 1), np.float32), w1, w2], 1)
+    a, b = gpu.eval_bsdf(p2, g2), gpu.eval_bsdf_literal(p2, g2)
+    assert np.isfinite(b).all() and np.array_equal(a, b)
+    assert (np.abs(a - oracle.eval_bsdf(p2, g2)) / np.maximum(np.abs(b).max(1, keepdims=True), 1e-4)).max() <= 1e-5
+
+
 def test_clearcoat_lobe_behaves_like_reference(gpu):
     # microfacet.py:68-71: sqrt(alpha**(2-2u) - 1) is NaN for alpha < 1 -> cosoh = max(0, NaN) = 0 -> invalid sample (zeros)
     rng = np.random.default_rng(13)
