@@ -298,6 +298,11 @@ __global__ void __launch_bounds__(1024) k_build_list(float4* __restrict__ tlo, i
     }
     if (threadIdx.x == 0) scal[11] = s_count;
 }
+// slot_of[face] of a listed triangle carries its list index + 1 above the slot (PTB_SLOT_LIST_SHIFT, ptb_traverse.cuh); after k_pack_tris
+__global__ void k_tag_listed(const int* __restrict__ list, const int* __restrict__ scal, const int* __restrict__ leaf, int* slot_of) {
+    const int j = threadIdx.x;
+    if (j < min(scal[11], PTB_LIST_CAP)) { const int s = list[j]; slot_of[leaf[s]] = s | ((j + 1) << PTB_SLOT_LIST_SHIFT); }
+}
 // traversal boxes, level by level (`ready` holds the sweep in which the reference box of a node was completed, so the children
 // of a node of level `stamp` belong to earlier levels): union of the inflated bounds of the unlisted leaves below the node.
 // Empty = (lo, hi) = (+1e30, -1e30).
@@ -837,6 +842,7 @@ int ptb_lbvh_build(ptb_ctx* c) {
         }
     }
     if (n > 0) { k_pack_tris<<<nblk(n), BLK, 0, st>>>(c->d_verts, c->d_leaf, n, c->d_tris, c->d_slot_of); c->launches++; }
+    if (n > 1) { k_tag_listed<<<1, PTB_LIST_CAP, 0, st>>>(c->d_list, c->d_scalars, c->d_leaf, c->d_slot_of); c->launches++; }
     PTB_CUDA(cudaEventRecord(e1, st));
     {
         int h_scal[16];

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLK) k_trace_simple(TraceScene S, IO
         if (idx < count) {
             RayIn in;
             fetch_direct(io, idx, &in);
-            const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
+            const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot & PTB_SLOT_MASK] : -1;
             HitRec h;
             if (POLICY == 0) {
                 h = trace_reference<COUNT>(S, in.ro, in.rd, avoid, &C);
@@ -157,25 +157,53 @@ PTB_D bool list_gate_ok(const TraceScene& S, const float4 (*s_gate)[2], int j, i
     float gl; bool gsure;
     return slab_cons2(glo.x, glo.y, glo.z, ghi.x, ghi.y, ghi.z, R, &gl, &gsure) && (gsure || gate_passes(S, S.gate[slot], ro, rd));
 }
-// The list is scanned in two phases.  Phase 1 (list_candidates, uniform control flow: every lane looks at the same entry, broadcast
-// shared-memory reads, no branches): the conservative slab test of the entry's INFLATED bounds -- the leaf bound of ptb_traverse.cuh,
+// The list is scanned in two phases.  Phase 1 (list_candidates, uniform control flow: every lane looks at the same box, broadcast
+// shared-memory reads, no branches): the conservative slab test of the entries' INFLATED bounds -- the leaf bound of ptb_traverse.cuh,
 // the same test a tree leaf gets from its parent's node step -- marks the entries whose triangle the ray can possibly be accepted by
 // (an ill-conditioned entry has no bound and is always marked).  Inside a room that is the two triangles of the wall the ray leaves
-// through, not all ten.  Phase 2 (list_scan): every lane walks its OWN marked entries (per-lane shared-memory index) with the exact
-// triangle test.  Before, all lanes ran the exact test on all entries, and its early exits (plane behind the ray, beyond the best hit)
-// left 20 of 32 lanes active in the long part.
+// through, not all ten.  The two triangles of an axis-aligned wall quad have the SAME bounds, so the block's prologue (list_setup)
+// reduces the list to its distinct boxes, each with the bit mask of the entries it stands for: five slab tests for the ten walls of a
+// Cornell room, and a passing box ORs its mask in (no per-entry work; the entry to avoid is cleared afterwards from the tag in the
+// avoid field, PTB_SLOT_LIST_SHIFT).  Phase 2 (list_scan): every lane walks its OWN marked entries (per-lane shared-memory index) with
+// the exact triangle test.  Before, all lanes ran the exact test on all entries, and its early exits (plane behind the ray, beyond the
+// best hit) left 20 of 32 lanes active in the long part.
 #ifndef PTB_LIST_FILTER
 #define PTB_LIST_FILTER 1           /* 0: every entry is a candidate (A/B builds) */
 #endif
-PTB_D unsigned list_candidates(const int* s_slot, const float4 (*s_box)[2], int nlist, int avoid_slot, const RayCons& R, const RayTrav& Q, float cull) {
-    unsigned cand = 0;
-    for (int j = 0; j < nlist; j++) {
-        const float4 lo = s_box[j][0], hi = s_box[j][1];
-        float lb;
-        const bool ok = !PTB_LIST_FILTER || (slab_trav(lo, hi, R, Q, &lb) && !(lb > cull));
-        const bool c = s_slot[j] != avoid_slot && (ok || (__float_as_int(lo.w) & PTB_TF_MUST) != 0);
-        cand |= c ? (1u << j) : 0u;
+struct ListBoxes { float4 box[PTB_LIST_CAP][2]; unsigned mask[PTB_LIST_CAP]; int nuniq; unsigned must, all; };
+// one warp of the block: distinct boxes of s_box[0..nlist) in order of first appearance, and for each the entries that share it
+PTB_D void list_setup(const float4 (*s_box)[2], int nlist, ListBoxes* U) {
+    const int j = threadIdx.x;                           // called by threads 0..31
+    const bool in = j < nlist;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (in) { a = s_box[j][0]; b = s_box[j][1]; }
+    int g = j;
+    for (int k = 0; k < j && in; k++) {
+        const float4 c = s_box[k][0], d = s_box[k][1];
+        if (a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z) { g = k; break; }
     }
+    const unsigned leaders = __ballot_sync(0xffffffffu, in && g == j);
+    const unsigned must = __ballot_sync(0xffffffffu, in && (__float_as_int(a.w) & PTB_TF_MUST) != 0);
+    if (in && g == j) {
+        const int u = __popc(leaders & ((1u << j) - 1u));
+        U->box[u][0] = a; U->box[u][1] = b; U->mask[u] = 0u;
+    }
+    __syncwarp();
+    if (in) atomicOr(&U->mask[__popc(leaders & ((1u << g) - 1u))], 1u << j);
+    if (j == 0) { U->nuniq = __popc(leaders); U->must = must; U->all = nlist >= 32 ? 0xffffffffu : (1u << nlist) - 1u; }
+}
+PTB_D unsigned list_candidates(const ListBoxes& U, int avoid_slot, const RayCons& R, const RayTrav& Q, float cull) {
+    unsigned cand = PTB_LIST_FILTER ? U.must : U.all;
+    if (PTB_LIST_FILTER) {
+        const int nu = U.nuniq;
+        for (int k = 0; k < nu; k++) {
+            float lb;
+            const bool ok = slab_trav(U.box[k][0], U.box[k][1], R, Q, &lb) && !(lb > cull);
+            if (ok) cand |= U.mask[k];
+        }
+    }
+    const int tag = avoid_slot >> PTB_SLOT_LIST_SHIFT;  // 0 (not listed, or no triangle to avoid: -1 >> 24 = -1 is excluded below) or list index + 1
+    if (avoid_slot >= 0 && tag != 0) cand &= ~(1u << (tag - 1));
     return cand;
 }
 // Closest accepted triangle among the marked entries (ties: larger slot) into ret / best; ANYHIT: stop at the first one.  GATED = false
@@ -217,6 +245,7 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
     __shared__ float4 s_tri[PTB_LIST_CAP][4];
     __shared__ float4 s_gate[PTB_LIST_CAP][2];
     __shared__ float4 s_box[PTB_LIST_CAP][2];          // inflated bounds (lo.w: PTB_TF_* flags)
+    __shared__ ListBoxes s_uniq;                       // their distinct boxes (list_setup)
     const int nlist = min(S.nlist, PTB_LIST_CAP);
     for (int j = threadIdx.x; j < nlist * 4; j += 256) {
         const int slot = S.list[j >> 2];
@@ -226,6 +255,8 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
         if ((j & 3) == 3) s_box[j >> 2][1] = S.thi[slot];
         if ((j & 3) == 0) s_slot[j >> 2] = slot;
     }
+    __syncthreads();
+    if (threadIdx.x < 32) list_setup(s_box, nlist, &s_uniq);
     __syncthreads();
     const int rounded = (count + 255) & ~255;          // every thread of a block runs the same number of iterations
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < rounded; idx += gridDim.x * 256) {
@@ -246,7 +277,7 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
             if (COUNT) nrays++;
             if (ray_is_special(in.ro, in.rd)) {
                 // axis-parallel / non-finite: exact tests over the reference's own arrays (rare)
-                const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot] : -1;
+                const int avoid = in.avoid_slot >= 0 ? S.leaf[in.avoid_slot & PTB_SLOT_MASK] : -1;
                 ret = trace_ordered<ANYHIT, COUNT>(S, in.ro, in.rd, avoid, in.tmax, &C);
                 io.store(in.item, ret, in.c);
             } else {
@@ -256,7 +287,7 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
                 int jw = -1;
                 delta = trav_delta(in.ro, S.scene_abs);
                 const RayTrav Q = ray_trav(R, delta);
-                const unsigned cand = list_candidates(s_slot, s_box, nlist, in.avoid_slot, R, Q, best + best * PTB_CULL_GUARD);
+                const unsigned cand = list_candidates(s_uniq, in.avoid_slot, R, Q, best + best * PTB_CULL_GUARD);
                 if (COUNT) C.boxes += nlist;
                 bool occluded = list_scan<ANYHIT, false, COUNT>(S, s_slot, s_tri, s_gate, cand, in, R, ret, best, &jw, C);
                 if (ret.hit && !list_gate_ok(S, s_gate, jw, ret.slot, R, in.ro, in.rd)) {

@@ -30,6 +30,12 @@ struct __align__(16) Node64 { float4 a, b, c, d; };
 #define PTB_TF_MUST 2
 #define PTB_TF_BIG 4
 #define PTB_TF_LISTED 8
+// slot_of[face] and the avoid field of the ray queues: the leaf slot in the low 24 bits (faces < 2^24, ptb_create); for a triangle on
+// the always-test list, its list index + 1 in bits 24..29 (lbvh.cu k_tag_listed), so that k_trace_pre gets the entry to skip from a
+// shift instead of comparing every entry's slot.  A tagged value never equals a tree leaf's slot (listed triangles are not in the
+// traversal tree), so the tree kernels compare it as it is; code that indexes by slot masks it.
+#define PTB_SLOT_MASK 0x00FFFFFF
+#define PTB_SLOT_LIST_SHIFT 24
 // 64-byte packed triangle, indexed by sorted leaf slot:
 //   a = (v0.xyz, 1/D)  b = (u.xyz, uu)  c = (v.xyz, uv)  d = (n.xyz, vv)     u=v1-v0, v=v2-v0, n=u x v, D = uv*uv - uu*vv
 // Every field is the f32 expression geometries.py:121-141 evaluates per test (they depend on the triangle only), so
@@ -366,7 +372,7 @@ PTB_D HitRec trace_ordered(const TraceScene& S, V3 ro, V3 rd, int avoid, float t
     if (COUNT) C->boxes++;
     // the root's own box (the reference pops and tests it first)
     if (!slab_fast(S.bmin[0], S.bmin[1], S.bmin[2], S.bmax[0], S.bmax[1], S.bmax[2], P, &nr)) return ret;
-    const int avoid_slot = avoid >= 0 ? S.slot_of[avoid] : -1;
+    const int avoid_slot = avoid >= 0 ? (S.slot_of[avoid] & PTB_SLOT_MASK) : -1;
     float best = ANYHIT ? fminf(tmax, PTB_INF) : PTB_INF;
     const float cull = PTB_INF * 4.0f;        // nothing is culled by distance
     int stack_id[PTB_STACK];
