@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     TraceCounters C; C.nodes = C.boxes = C.tris = 0; C.max_stack = 0;
     unsigned long long nrays = 0;
-    __shared__ int s_warp[8], s_base;
+    __shared__ int s_warp[2][8], s_base[2];
+    int par = 0;
     // the always-test list in shared memory: slots, packed triangles, gate boxes (broadcast reads, no dependent global loads)
     __shared__ int s_slot[PTB_LIST_CAP];
     __shared__ float4 s_tri[PTB_LIST_CAP][4];
@@ -309,18 +310,19 @@ __global__ void __launch_bounds__(256) k_trace_pre(TraceScene S, IO io, const in
             }
         }
         // append the survivors to the tree queue: one atomic per block (every launch hammers the same counter), contiguous records
+        // (two sets of buffers used alternately: no third barrier, see block_append)
         const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) s_warp[warp] = __popc(m);
+        if (lane == 0) s_warp[par][warp] = __popc(m);
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
-            s_base = tot ? atomicAdd(tree_count, tot) : 0;
+            for (int w = 0; w < 8; w++) { const int c = s_warp[par][w]; s_warp[par][w] = tot; tot += c; }
+            s_base[par] = tot ? atomicAdd(tree_count, tot) : 0;
         }
         __syncthreads();
-        const int wbase = s_base + s_warp[warp];
-        __syncthreads();
+        const int wbase = s_base[par] + s_warp[par][warp];
+        par ^= 1;
         if (live) {
             const int pos = wbase + __popc(m & ((1u << lane) - 1u));
             xq.e[0][pos] = make_float4(in.ro.x, in.ro.y, in.ro.z, __int_as_float(in.item));

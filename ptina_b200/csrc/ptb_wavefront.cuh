@@ -53,8 +53,11 @@ struct RngRun {
 };
 
 // ---- queue append: warp ballot + block prefix, one atomic per block, contiguous (coalesced) writes -------------
-// returns the queue position reserved for this thread (-1 if !flag)
-template <int NT>
+// returns the queue position reserved for this thread (-1 if !flag).
+// TAIL_SYNC = false: the caller alternates between two sets of shared buffers from one call to the next, which makes the trailing
+// barrier (it only protects the buffers against the NEXT call's writes) unnecessary: a warp can reach the writes of call k+2 only after
+// the barriers of call k+1, which every warp passes after its reads of call k.
+template <int NT, bool TAIL_SYNC = true>
 PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     unsigned m = __ballot_sync(0xffffffffu, flag);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -69,12 +72,12 @@ PTB_D int block_append(bool flag, int* counter, int* s_warp, int* s_base) {
     }
     __syncthreads();
     int pos = flag ? *s_base + s_warp[w] + rank : -1;
-    __syncthreads();
+    if (TAIL_SYNC) __syncthreads();
     return pos;
 }
 
 // two queues at once (next extend queue + shadow queue): one 64-bit atomic per block on the adjacent counters (n_out, n_shadow)
-template <int NT>
+template <int NT, bool TAIL_SYNC = true>
 PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 * NT/32] */, unsigned long long* s_base, int* pa, int* pb) {
     const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -90,7 +93,7 @@ PTB_D void block_append2(bool fa, bool fb, int* counter_pair, int* s_warp /* [2 
     const unsigned long long base = *s_base;
     *pa = fa ? (int)(unsigned)base + s_warp[w] + __popc(ma & ((1u << lane) - 1u)) : -1;
     *pb = fb ? (int)(unsigned)(base >> 32) + s_warp[NT / 32 + w] + __popc(mb & ((1u << lane) - 1u)) : -1;
-    __syncthreads();
+    if (TAIL_SYNC) __syncthreads();
 }
 
 // ---- model.py:88-101 get_geometries + geometries.py:96-108 -------------------------------------------------------------------

@@ -42,8 +42,10 @@ template <int ENGINE>
 __global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
-    __shared__ int s_warp[SBLK / 32]; __shared__ int s_base;
-    __shared__ int s_warp2[2 * (SBLK / 32)]; __shared__ unsigned long long s_base2;
+    // two sets of append buffers, used alternately (block_append: no trailing barrier)
+    __shared__ int s_warp[2][SBLK / 32]; __shared__ int s_base[2];
+    __shared__ int s_warp2[2][2 * (SBLK / 32)]; __shared__ unsigned long long s_base2[2];
+    int par = 0;
     const int count = ctrl->n_in;
     const int rounded = (count + SBLK - 1) / SBLK * SBLK;
     for (int i0 = blockIdx.x * SBLK; i0 < rounded; i0 += gridDim.x * SBLK) {
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* 
 #endif
         }
         int pos, ps = -1;
-        if (ENGINE == PTB_ENGINE_PATH) block_append2<SBLK>(alive, want_shadow, &ctrl->n_out, s_warp2, &s_base2, &pos, &ps);
-        else pos = block_append<SBLK>(alive, &ctrl->n_out, s_warp, &s_base);
+        if (ENGINE == PTB_ENGINE_PATH) block_append2<SBLK, false>(alive, want_shadow, &ctrl->n_out, s_warp2[par], &s_base2[par], &pos, &ps);
+        else pos = block_append<SBLK, false>(alive, &ctrl->n_out, s_warp[par], &s_base[par]);
+        par ^= 1;
         if (alive) {
             q_out.o[pos] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float(p));
             q_out.d[pos] = make_float4(next_d.x, next_d.y, next_d.z, __int_as_float(avoid_slot));   // avoid = hit.index (as its leaf slot)
