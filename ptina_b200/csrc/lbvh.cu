@@ -626,12 +626,14 @@ __global__ void __launch_bounds__(BLK) k_quant_nodes(const Node64* __restrict__ 
         }
     }
     if (bad) atomicAdd(&scal[14], 1);
-    qnodes[2 * i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
-    qnodes[2 * i + 1] = make_uint4(f[8] | (f[9] << 16), f[10] | (f[11] << 16), (unsigned)id0, (unsigned)id1);
+    // one word per axis and box: lo in the low half, hi in the high half (the traversal picks the entry / exit plane of an axis out of
+    // ONE word with a per-ray PRMT selector, ptb_traverse.cuh slab_quant)
+    qnodes[2 * i] = make_uint4(f[0] | (f[3] << 16), f[1] | (f[4] << 16), f[2] | (f[5] << 16), f[6] | (f[9] << 16));
+    qnodes[2 * i + 1] = make_uint4(f[7] | (f[10] << 16), f[8] | (f[11] << 16), (unsigned)id0, (unsigned)id1);
 }
 
 // 4-wide quantised node of binary node i (64 B): its two children, each internal one replaced by ITS two children -- up to four
-// (box, id) entries on the same 15-bit grid as Node32 (three words per box, low half first: (lo.x lo.y) (lo.z hi.x) (hi.y hi.z)), then
+// (box, id) entries on the same 15-bit grid as Node32 (three words per box, one per axis: lo in the low half, hi in the high half), then
 // the four ids (-1: none).  Every binary node gets one (index = binary index); a traversal from the root only ever reaches those at
 // even depth, so the hot footprint equals the binary quantised array's.
 __global__ void __launch_bounds__(BLK) k_wide4_nodes(const Node64* __restrict__ nodes, int n, QuantGrid g, uint4* __restrict__ wnodes, int* __restrict__ scal) {
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(BLK) k_wide4_nodes(const Node64* __restrict__ 
             f[a] = quant_plane(used ? lo[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], false, used ? &bad : &dummy);
             f[3 + a] = quant_plane(used ? hi[k][a] : g.base[a] + g.ext[a], g.base[a], g.ext[a], true, used ? &bad : &dummy);
         }
-        w[3 * k] = f[0] | (f[1] << 16); w[3 * k + 1] = f[2] | (f[3] << 16); w[3 * k + 2] = f[4] | (f[5] << 16);
+        w[3 * k] = f[0] | (f[3] << 16); w[3 * k + 1] = f[1] | (f[4] << 16); w[3 * k + 2] = f[2] | (f[5] << 16);
         w[12 + k] = used ? (unsigned)id[k] : 0xFFFFFFFFu;
     }
     if (bad) atomicAdd(&scal[14], 1);

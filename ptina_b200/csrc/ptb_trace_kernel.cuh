@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     int item = -1, avoid_slot = -1;            // item >= 0: this lane owns a ray (its result is stored when the lane next goes idle)
     RayCons R; R.o = v3s(0.0f); R.d = v3s(0.0f); R.r = v3s(0.0f); R.nc = v3s(0.0f); R.a2 = 0.0f;
     RayTrav Q; Q.nc1 = v3s(0.0f); Q.nc2 = v3s(0.0f);   // slab constants of the traversal-tree boxes (ray_trav)
-    RayQuant G; G.A = v3s(0.0f); G.B1 = v3s(0.0f); G.B2 = v3s(0.0f);      // the same for quantised nodes (ray_quant)
+    RayQuant G; G.A = v3s(0.0f); G.Bn = v3s(0.0f); G.Bf = v3s(0.0f); G.sx = G.sy = G.sz = PTB_QSEL_LO;      // the same for quantised nodes (ray_quant)
     V3 contrib = v3s(0.0f);
     float best = 0.0f, cull = 0.0f;
     HitRec ret; ret.hit = 0; ret.depth = PTB_INF; ret.index = -1; ret.u = 0.0f; ret.v = 0.0f; ret.slot = -1;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         float nk;
-                        bool hk = slab_quant(quant_lo(bw[3 * k]), quant_hi(bw[3 * k]), quant_lo(bw[3 * k + 1]), quant_hi(bw[3 * k + 1]), quant_lo(bw[3 * k + 2]), quant_hi(bw[3 * k + 2]), G, R.a2, &nk);
+                        bool hk = slab_quant(bw[3 * k], bw[3 * k + 1], bw[3 * k + 2], G, R.a2, &nk);
                         hk = hk && wid[k] >= 0;
                         const int ck = wid[k] & PTB_NODE_ID;
                         if (wid[k] & PTB_NODE_MUST) nk = 0.0f;        // an ill-conditioned triangle below: no distance bound holds
@@ -590,8 +590,8 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                         if constexpr (SMEM) { qa = reinterpret_cast<const uint4*>(s_node)[cur]; qb = reinterpret_cast<const uint4*>(s_node)[(n - 1) + cur]; }
                         else ld_qnode256(S.qnodes + 2 * cur, &qa, &qb);
                         w0 = (int)qb.z; w1 = (int)qb.w;
-                        h0 = slab_quant(quant_lo(qa.x), quant_hi(qa.x), quant_lo(qa.y), quant_hi(qa.y), quant_lo(qa.z), quant_hi(qa.z), G, R.a2, &n0);
-                        h1 = slab_quant(quant_lo(qa.w), quant_hi(qa.w), quant_lo(qb.x), quant_hi(qb.x), quant_lo(qb.y), quant_hi(qb.y), G, R.a2, &n1);
+                        h0 = slab_quant(qa.x, qa.y, qa.z, G, R.a2, &n0);
+                        h1 = slab_quant(qa.w, qb.x, qb.y, G, R.a2, &n1);
                     }
                     if (COUNT) { C.nodes++; C.boxes += 2; }
                     h0 = h0 && w0 >= 0; h1 = h1 && w1 >= 0;

@@ -280,8 +280,15 @@ PTB_D bool tri_fast(const Tri64& T, V3 ro, V3 rd, float tlimit, float* depth, fl
 // with 0x3F000000 turns it into the f32 v, and the plane is never formed: with A = qext * r (exact, qext is a power of two) and
 // B = fma(qbase, r, nc) the slab distance is fma(v, A, B) -- the product is exact, so against fma(plane, r, nc) the only new
 // error is the rounding of B, at most u|B| per plane, which ray_quant folds into B itself.
-//   words 0-5: (lo0.x lo0.y) (lo0.z hi0.x) (hi0.y hi0.z) (lo1.x lo1.y) (lo1.z hi1.x) (hi1.y hi1.z), low half first; 6, 7: child ids
-struct RayQuant { V3 A, B1, B2; };
+//   words 0-5: one per box and axis, (lo | hi << 16): box 0 x, y, z, box 1 x, y, z; 6, 7: child ids
+// Which of an axis' two planes the ray enters through is a property of the ray (the sign of 1/d), so nothing has to be compared per
+// box: a per-ray PRMT selector takes the entry plane's field out of the axis' word, its complement the exit plane's, and the slab
+// distances are max3 / min3 of three FMAs each.  Same values as min / max of the two distances per axis: for r > 0, lo <= hi, A > 0 and
+// B(lo) <= B(hi) make the lo plane's distance the smaller one by the monotonicity of the FMA, and the other way round for r < 0.
+struct RayQuant { V3 A, Bn, Bf; unsigned sx, sy, sz; };        // Bn / Bf: constants of the entry / exit planes; s*: PRMT selector of the entry plane
+#define PTB_QSEL_LO 0x7104u
+#define PTB_QSEL_HI 0x7324u
+#define PTB_QSEL_FLIP 0x0220u
 PTB_D RayQuant ray_quant(const TraceScene& S, const RayCons& R, const RayTrav& Q) {
     RayQuant G;
     G.A = mk3(S.qext[0] * R.r.x, S.qext[1] * R.r.y, S.qext[2] * R.r.z);
@@ -292,18 +299,24 @@ PTB_D RayQuant ray_quant(const TraceScene& S, const RayCons& R, const RayTrav& Q
     const V3 k = mk3(copysignf(K4, R.r.x), copysignf(K4, R.r.y), copysignf(K4, R.r.z));
     V3 b1 = mk3(__fmaf_rn(S.qbase[0], R.r.x, Q.nc1.x), __fmaf_rn(S.qbase[1], R.r.y, Q.nc1.y), __fmaf_rn(S.qbase[2], R.r.z, Q.nc1.z));
     V3 b2 = mk3(__fmaf_rn(S.qbase[0], R.r.x, Q.nc2.x), __fmaf_rn(S.qbase[1], R.r.y, Q.nc2.y), __fmaf_rn(S.qbase[2], R.r.z, Q.nc2.z));
-    G.B1 = mk3(__fmaf_rn(-k.x, fabsf(b1.x), b1.x), __fmaf_rn(-k.y, fabsf(b1.y), b1.y), __fmaf_rn(-k.z, fabsf(b1.z), b1.z));
-    G.B2 = mk3(__fmaf_rn(k.x, fabsf(b2.x), b2.x), __fmaf_rn(k.y, fabsf(b2.y), b2.y), __fmaf_rn(k.z, fabsf(b2.z), b2.z));
+    const V3 B1 = mk3(__fmaf_rn(-k.x, fabsf(b1.x), b1.x), __fmaf_rn(-k.y, fabsf(b1.y), b1.y), __fmaf_rn(-k.z, fabsf(b1.z), b1.z));      // lo planes
+    const V3 B2 = mk3(__fmaf_rn(k.x, fabsf(b2.x), b2.x), __fmaf_rn(k.y, fabsf(b2.y), b2.y), __fmaf_rn(k.z, fabsf(b2.z), b2.z));         // hi planes
+    const bool px = !(R.r.x < 0.0f), py = !(R.r.y < 0.0f), pz = !(R.r.z < 0.0f);
+    G.Bn = mk3(px ? B1.x : B2.x, py ? B1.y : B2.y, pz ? B1.z : B2.z);
+    G.Bf = mk3(px ? B2.x : B1.x, py ? B2.y : B1.y, pz ? B2.z : B1.z);
+    G.sx = px ? PTB_QSEL_LO : PTB_QSEL_HI; G.sy = py ? PTB_QSEL_LO : PTB_QSEL_HI; G.sz = pz ? PTB_QSEL_LO : PTB_QSEL_HI;
     return G;
 }
-PTB_D float quant_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7104)); }
-PTB_D float quant_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7324)); }
-PTB_D bool slab_quant(float lx, float ly, float lz, float hx, float hy, float hz, const RayQuant& G, float a2, float* lb) {
-    const float x1 = __fmaf_rn(lx, G.A.x, G.B1.x), x2 = __fmaf_rn(hx, G.A.x, G.B2.x);
-    const float y1 = __fmaf_rn(ly, G.A.y, G.B1.y), y2 = __fmaf_rn(hy, G.A.y, G.B2.y);
-    const float z1 = __fmaf_rn(lz, G.A.z, G.B1.z), z2 = __fmaf_rn(hz, G.A.z, G.B2.z);
-    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), 0.0f));
-    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), PTB_INF));
+PTB_D float quant_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, PTB_QSEL_LO)); }
+PTB_D float quant_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x3F000000u, PTB_QSEL_HI)); }
+PTB_D float quant_sel(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x3F000000u, sel)); }
+// box = the three axis words of a Node32 / wide-node entry
+PTB_D bool slab_quant(unsigned wx, unsigned wy, unsigned wz, const RayQuant& G, float a2, float* lb) {
+    const float xn = __fmaf_rn(quant_sel(wx, G.sx), G.A.x, G.Bn.x), xf = __fmaf_rn(quant_sel(wx, G.sx ^ PTB_QSEL_FLIP), G.A.x, G.Bf.x);
+    const float yn = __fmaf_rn(quant_sel(wy, G.sy), G.A.y, G.Bn.y), yf = __fmaf_rn(quant_sel(wy, G.sy ^ PTB_QSEL_FLIP), G.A.y, G.Bf.y);
+    const float zn = __fmaf_rn(quant_sel(wz, G.sz), G.A.z, G.Bn.z), zf = __fmaf_rn(quant_sel(wz, G.sz ^ PTB_QSEL_FLIP), G.A.z, G.Bf.z);
+    const float tn = fmaxf(fmaxf(xn, yn), fmaxf(zn, 0.0f));
+    const float tf = fminf(fminf(xf, yf), fminf(zf, PTB_INF));
     const float l = __fmaf_rn(tn, 1.0f - PTB_CONS_KAPPA, -a2);
     const float ub = __fmaf_rn(fabsf(tf), PTB_CONS_KAPPA, tf);
     *lb = l;

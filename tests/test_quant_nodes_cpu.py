@@ -103,6 +103,8 @@ def test_folded_slab_brackets_the_decoded_planes():
     od, dd = o.astype(np.float64), d.astype(np.float64)
     t1 = (float(base) + vl.astype(np.float64) * float(ext) - od) / dd
     t2 = (float(base) + vh.astype(np.float64) * float(ext) - od) / dd
+    # slab_quant takes the entry / exit plane by the sign of r instead of min / max of the two distances: the same values
+    assert np.array_equal(np.where(r > 0, x1, x2), np.minimum(x1, x2)) and np.array_equal(np.where(r > 0, x2, x1), np.maximum(x1, x2))
     near_c, far_c = np.minimum(x1, x2).astype(np.float64), np.maximum(x1, x2).astype(np.float64)
     near_t, far_t = np.minimum(t1, t2), np.maximum(t1, t2)
     assert np.all(near_c <= near_t) and np.all(far_c >= far_t)
