@@ -583,10 +583,12 @@ def run_gpu(args):
             trav_ms = st4['extend'] + st4['shadow']
             alg = 64.0 * c4['node_visits'] + 48.0 * c4['tri_tests'] + 48.0 * c4['rays']
             l2 = ctx.measure_l2(64, 20)
-            fmt = 32.0 * c4['node_visits'] + 64.0 * c4['tri_tests'] + 48.0 * c4['rays']
+            wide4 = os.environ.get('PTB_NO_WIDE4') is None       # trees walked out of global memory use 4-wide 64-byte nodes unless switched off
+            fmt = (64.0 if wide4 else 32.0) * c4['node_visits'] + 64.0 * c4['tri_tests'] + 48.0 * c4['rays']
             r['roofline_l2'] = {'bound': 'l2', 'achieved': alg / (trav_ms * 1e-3) / 1e9, 'peak': l2, 'unit': 'GB/s', 'frac': alg / (trav_ms * 1e-3) / 1e9 / l2,
                                 'formula': 'SURVEY 8(d): 64 B x node visits + 48 B x triangle tests + 48 B x rays, counters_per_step / (extend + shadow stage time, serial pass)',
-                                'bytes_in_this_format': fmt, 'format_note': 'nodes are fetched as 32-B quantised Node32 (one 256-bit load), triangles as 64-B Tri64',
+                                'bytes_in_this_format': fmt, 'format_note': ('a node visit is one 4-wide quantised node: 64 B, two 256-bit loads, up to four child boxes' if wide4 else 'nodes are fetched as 32-B quantised Node32 (one 256-bit load)') + '; triangles as 64-B Tri64',
+                                'note': 'not the binding roof: the kernel waits on dependent fetches and on instruction issue (roofline_issue next to this); wider nodes and a better tree LOWER this numerator (fewer visits per ray) while the frame gets faster',
                                 'counters_per_step': {k: c4[k] for k in ('rays', 'node_visits', 'tri_tests')}, 'traversal_ms_per_step': trav_ms,
                                 'peak_source': 'ptb_measure_l2: 148 x 8 blocks x 256 threads stream a 64 MiB buffer 20 times with 16-byte ld.global.cg loads after 2 warm passes (CUDA events)'}
         # the full config: 1024 spp, Sobol points 65..1088, sharded, one reduce at the end
@@ -616,6 +618,13 @@ def run_gpu(args):
                     r = issue_roofline(name, configs[key]['spp_per_step_total'] / world, configs[key]['ms_per_step'], clocks.get('sm_mhz'))   # per GPU
                     r.pop('per_kernel', None)
                     configs[key]['roofline'] = r
+            if 'config4_mega' in configs:
+                # config 4 next to its L2 roofline: the kernel is bound by dependent-fetch latency and instruction issue, not by L2 bytes
+                # (a 4-wide step fetches 64 B for what two or three binary steps fetched before, so the byte numerator FALLS as the kernel
+                # gets faster); the issue-slot view uses the instruction count of a 4-spp step (profiles/inst_counts.json), scaled by spp
+                r = issue_roofline('mega', configs['config4_mega']['spp_per_step_total'] / world, configs['config4_mega']['ms_per_step'], clocks.get('sm_mhz'))
+                r.pop('per_kernel', None)
+                configs['config4_mega']['roofline_issue'] = r
         # the schema's HBM view of the traversal stages, with SURVEY 8(d)'s formula (served from shared memory / L1, so not the binding roof)
         trav_ms = stage['extend'] + stage['shadow']
         alg = 64.0 * cnt['node_visits'] + 48.0 * cnt['tri_tests'] + 48.0 * cnt['rays']

@@ -29,7 +29,10 @@
 #define PTB_POOL 64                 /* queue positions a warp reserves per atomic */
 #endif
 #ifndef PTB_FETCH_MIN
-#define PTB_FETCH_MIN 8             /* idle lanes that trigger a refill from the staged tile */
+#define PTB_FETCH_MIN 8             /* idle lanes that trigger a refill from the staged tile: resident trees */
+#endif
+#ifndef PTB_FETCH_MIN_G
+#define PTB_FETCH_MIN_G 4           /* the same for trees walked out of global memory (a ray lives longer there, so an idle lane costs more: +1.3 % on config 4) */
 #endif
 
 struct RayIn { int item; V3 ro, rd; int avoid_slot; float tmax; V3 c; };
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
         const bool leaf_ok = q_count > 0;
         const unsigned mn = __ballot_sync(FULL, node_ok), ml = __ballot_sync(FULL, leaf_ok);
         const unsigned idle = ~(mn | ml);
-        if (!exhausted && (__popc(idle) >= PTB_FETCH_MIN || idle == FULL)) {
+        if (!exhausted && (__popc(idle) >= (SMEM ? PTB_FETCH_MIN : PTB_FETCH_MIN_G) || idle == FULL)) {
             // ---- idle lanes store their result and take the next staged records ----------------------------------------------------------
             if (!tile_ready) { cp_async_wait<1>(); __syncwarp(); tile_ready = true; }     // the older of the two groups in flight has landed
             const int nv = cur_buf == 0 ? tile_n0 : tile_n1;
