@@ -35,11 +35,14 @@ __global__ void k_prepare_cache(const SceneParams* __restrict__ P, const float4*
 #define PTB_SHADE_BLK 512
 #endif
 constexpr int SBLK = PTB_SHADE_BLK;
+#ifndef PTB_SHADE_MINB
+#define PTB_SHADE_MINB (1024 / PTB_SHADE_BLK)      /* resident blocks per SM the kernel is compiled for (register cap = 65536 / threads) */
+#endif
 #ifndef PTB_SHADE_PF2
 #define PTB_SHADE_PF2 1          /* 1: prefetch the next iteration's path state into L1 (matball shade 4.65 -> 4.46 ms; config 2 unchanged), 0: off */
 #endif
 template <int ENGINE>
-__global__ void __launch_bounds__(SBLK, 1024 / SBLK) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
+__global__ void __launch_bounds__(SBLK, PTB_SHADE_MINB) k_shade(const SceneParams* __restrict__ P, const SceneCache* __restrict__ SC, const float4* __restrict__ texels, const float* __restrict__ verts,
                                                const int* __restrict__ mtlids, const int* __restrict__ slot_of, const float* __restrict__ rngtab, int dim, int rng_stride,
                                                FrameMap fm, PathState st, RayQueue q_in, RayQueue q_out, RayQueue q_shadow, Ctrl* ctrl) {
     // two sets of append buffers, used alternately (block_append: no trailing barrier)
@@ -229,7 +232,7 @@ void SHADE_FN(ptb_shade_prepare_cache)(ptb_ctx* c) {
 }
 
 void SHADE_FN(ptb_shade_launch)(ptb_ctx* c, const Lane& L, int engine, const float* rngtab, int dim, int rng_stride, const FrameMap& fm, int cur, cudaStream_t st) {
-    const int grid = c->sm_count * (1024 / SBLK);
+    const int grid = c->sm_count * PTB_SHADE_MINB;
     if (engine == PTB_ENGINE_PATH)
         k_shade<PTB_ENGINE_PATH><<<grid, SBLK, 0, st>>>(c->d_params, c->d_cache, c->d_texels, c->d_verts, c->d_mtlids, c->d_slot_of, rngtab, dim, rng_stride, fm, c->st,
                                                      L.xq[cur], L.xq[cur ^ 1], L.sq, L.ctrl);
