@@ -135,6 +135,7 @@ struct ptb_ctx {
     uint4* d_qnodes = nullptr;      // [2(n-1)] quantised copy of d_nodes (Node32), built for trees that are traversed out of global memory
     uint4* d_wnodes = nullptr;      // [4(n-1)] 4-wide quantised nodes (lbvh.cu k_wide4_nodes), global-memory trees only
     int wnodes_cap = 0; bool wnodes_ok = false;
+    bool s16_stack = true;          // PTB_NO_S16=1: resident tree kernels keep the 64-bit stack entries for shallow trees too
     bool wide4 = true;              // "wide4" / PTB_NO_WIDE4=1: walk big trees through the 4-wide nodes
     float qbase[3]{}, qext[3]{1.0f, 1.0f, 1.0f}, qinv[3]{1.0f, 1.0f, 1.0f};
     Tri64* d_tris = nullptr;

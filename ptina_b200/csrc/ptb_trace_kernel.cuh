@@ -412,9 +412,15 @@ struct TraceSmem {
 // CTAs per SM to cover the L2 latency.
 // W4 (global-memory variant only): 4-wide quantised nodes (lbvh.cu k_wide4_nodes: a binary node with its internal children replaced by
 // their children, 64 bytes) -- half as many dependent node fetches per ray, which is what the big-scene kernel waits for.
-template <class IO, bool COUNT, int BLK, bool SMEM, bool QN, bool W4 = false>
+// S16 (resident variants, traversal trees of height <= PTB_S16_DEPTH with fewer than 65536 nodes): the whole stack lives in the
+// shared-memory region as 32-bit entries -- node id in the low half, the entry distance cut to its upper 16 bits (bfloat16, rounded
+// toward zero after a clamp at 0: still a lower bound of any depth below, which is all a popped entry's distance is used for) -- so
+// a push is one STS, a pop one LDS, and the local-memory tail of the stack with its two branches is gone.
+#define PTB_S16_DEPTH 16
+template <class IO, bool COUNT, int BLK, bool SMEM, bool QN, bool W4 = false, bool S16 = false>
 __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(TraceScene S, IO io, ExpQ xq, int* cursor, const int* count_ptr, DevCounters* ctr) {
     static_assert(!W4 || (!SMEM && QN), "4-wide nodes: global-memory quantised variant only");
+    static_assert(!S16 || (SMEM && !W4 && PTB_S16_DEPTH * sizeof(unsigned) <= TraceSmem<BLK, W4>::sstack * sizeof(unsigned long long)), "S16: resident variants, same shared-memory region");
     using Smem = TraceSmem<BLK, W4>;
     constexpr int PQ = Smem::pq;
     constexpr bool ANYHIT = IO::kAnyHit;
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     // traversal stack, entries [0, SSTACK): column = thread
     constexpr int SSTACK = Smem::sstack;
     unsigned long long (*s_stack)[BLK] = reinterpret_cast<unsigned long long (*)[BLK]>(s_raw + Smem::tile + Smem::queue);
+    unsigned (*s_stack32)[BLK] = reinterpret_cast<unsigned (*)[BLK]>(s_raw + Smem::tile + Smem::queue);        // S16: the same region
     // resident nodes: quarter q of node i at s_node[q * (n-1) + i]
     float4* s_node = reinterpret_cast<float4*>(s_raw + Smem::fixed);
     if (SMEM) {
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
     // stack entries: low word = internal node, high word = lower bound of the depth of anything below it.  A pop is issued as soon
     // as a lane runs out of children (end of its node step) into `pe`, and consumed at the start of its next node step, so the
     // local-memory load has a whole iteration to land.
-    unsigned long long stack[PTB_STACK - SSTACK > 0 ? PTB_STACK - SSTACK : 1];      // entries beyond the shared-memory part
+    unsigned long long stack[(!S16 && PTB_STACK - SSTACK > 0) ? PTB_STACK - SSTACK : 1];      // entries beyond the shared-memory part
     unsigned long long pe = 0;                 // popped entry, valid iff `popped`
     bool popped = false;
     int sp = 0;
@@ -542,7 +549,11 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
 #pragma unroll 1
             for (int rep = 0; rep < PTB_NODE_REPS; rep++)
             if (rep == 0 ? node_ok : ((cur != -1 || popped) && q_count <= PQ - (W4 ? 4 : 2))) {
-                if (cur == -1) { cur = (int)(unsigned)pe; cur_near = __int_as_float((int)(pe >> 32)); popped = false; }
+                if (cur == -1) {
+                    if constexpr (S16) { cur = (int)((unsigned)pe & 0xffffu); cur_near = __uint_as_float((unsigned)pe & 0xffff0000u); }
+                    else { cur = (int)(unsigned)pe; cur_near = __int_as_float((int)(pe >> 32)); }
+                    popped = false;
+                }
                 if (cur_near > cull) cur = -1;          // nothing below can beat the best hit found since it was pushed / chosen
                 else if constexpr (W4) {
                     uint4 qa, qb, qc, qd;
@@ -611,8 +622,12 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     const bool first1 = !(n0 < n1);     // nearer first
                     if (d0 && d1) {
                         // a proper tree of height <= PTB_STACK cannot overflow (checked at build time)
-                        const unsigned long long entry = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
-                        if (sp < SSTACK) s_stack[sp][threadIdx.x] = entry; else stack[sp - SSTACK] = entry;
+                        if constexpr (S16) {
+                            s_stack32[sp][threadIdx.x] = (__float_as_uint(fmaxf(first1 ? n0 : n1, 0.0f)) & 0xffff0000u) | (unsigned)((first1 ? c0 : c1) - n);
+                        } else {
+                            const unsigned long long entry = ((unsigned long long)(unsigned)__float_as_int(first1 ? n0 : n1) << 32) | (unsigned)((first1 ? c0 : c1) - n);
+                            if (sp < SSTACK) s_stack[sp][threadIdx.x] = entry; else stack[sp - SSTACK] = entry;
+                        }
                         sp++;
                         if (COUNT) C.max_stack = max(C.max_stack, (unsigned)sp);
                         cur = (first1 ? c1 : c0) - n; cur_near = first1 ? n1 : n0;
@@ -620,7 +635,12 @@ __global__ void __launch_bounds__(BLK, SMEM ? 1 : PTB_TRACE_MINB) k_trace_tree(T
                     else if (d1) { cur = c1 - n; cur_near = n1; }
                     else cur = -1;
                 }
-                if (cur == -1 && sp > 0) { --sp; pe = sp < SSTACK ? s_stack[sp][threadIdx.x] : stack[sp - SSTACK]; popped = true; }      // out of children: issue the pop now
+                if (cur == -1 && sp > 0) {                                  // out of children: issue the pop now
+                    --sp;
+                    if constexpr (S16) pe = s_stack32[sp][threadIdx.x];
+                    else pe = sp < SSTACK ? s_stack[sp][threadIdx.x] : stack[sp - SSTACK];
+                    popped = true;
+                }
             }
         } else {
             // ---- leaf step: the oldest pending leaf of every lane that has one ---------------------------------------------------------------

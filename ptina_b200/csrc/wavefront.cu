@@ -350,12 +350,17 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
         const int mode = ptb_tree_mode(c, S.n);
         if (mode == PTB_TREE_RESIDENT) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
-            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false>;
+            // a traversal tree of height <= 16: the stack as 32-bit entries, all of it in shared memory (S16)
+            const bool s16 = c->s16_stack && c->tree_info.trav_depth >= 1 && c->tree_info.trav_depth <= PTB_S16_DEPTH && S.n <= 65536;
+            auto kern = s16 ? (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false, false, true>)
+                            : (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
             kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else if (mode == PTB_TREE_RESIDENT_QUANT) {
             // twice the size: resident as quantised 32-byte nodes
-            auto kern = c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>;
+            const bool s16 = c->s16_stack && c->tree_info.trav_depth >= 1 && c->tree_info.trav_depth <= PTB_S16_DEPTH && S.n <= 65536;
+            auto kern = s16 ? (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true, false, true>)
+                            : (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
             kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else if (S.wnodes) {
@@ -446,6 +451,7 @@ int ptb_wf_init(ptb_ctx* c) {
     c->use_ploc = getenv("PTB_NO_PLOC") == nullptr;
     c->ploc_big = getenv("PTB_NO_PLOC_BIG") == nullptr;
     c->wide4 = getenv("PTB_NO_WIDE4") == nullptr;
+    c->s16_stack = getenv("PTB_NO_S16") == nullptr;
     if (const char* r = getenv("PTB_PLOC_RADIUS")) { const int v = atoi(r); if (v >= 1 && v <= 1024) c->ploc_radius = v; }
     PTB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PTB_CUDA(cudaEventCreateWithFlags(&c->ev_shade, cudaEventDisableTiming));
