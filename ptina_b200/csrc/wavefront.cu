@@ -330,6 +330,16 @@ int ptb_tree_mode(const ptb_ctx* c, int n) {
     if (TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::qbvh(n) <= (size_t)c->smem_optin) return PTB_TREE_RESIDENT_QUANT;
     return PTB_TREE_GLOBAL;
 }
+// S16 (ptb_trace_kernel.cuh): can the traversal stack of this tree never hold more than PTB_S16_DEPTH entries?  An entry is pushed at
+// a node whose two children are both internal and both hit, so at a node of level L (root = 1) the stack holds at most L entries, and
+// such a node has at least two levels below it.  For the PLOC tree the build reports the height in internal-node levels along the
+// longest root-to-leaf path (leaves 0, a merge max + 1): at most height - 1 entries.  The LBVH topology's depth is the reference's own
+// count (lbvh.cu k_validate), taken as it is.
+static bool ptb_s16_ok(const ptb_ctx* c, int n) {
+    const int d = c->tree_info.trav_depth;
+    const int need = c->tree_info.trav_ploc ? d - 1 : d;
+    return c->s16_stack && d >= 1 && need <= PTB_S16_DEPTH && n <= 65536;
+}
 // one traversal launch: the persistent ordered kernel, or the literal reference-order kernel
 // which: 0 = extend, 1 = shadow / taps (selects the tree-queue counters of the control block, reset by k_ctrl_*)
 template <class IO>
@@ -351,14 +361,14 @@ static void launch_trace_io(ptb_ctx* c, const TraceScene& S, const IO& io, int p
         if (mode == PTB_TREE_RESIDENT) {
             // the packed BVH fits in shared memory: one CTA per SM keeps it resident
             // a traversal tree of height <= 16: the stack as 32-bit entries, all of it in shared memory (S16)
-            const bool s16 = c->s16_stack && c->tree_info.trav_depth >= 1 && c->tree_info.trav_depth <= PTB_S16_DEPTH && S.n <= 65536;
+            const bool s16 = ptb_s16_ok(c, S.n);
             auto kern = s16 ? (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false, false, true>)
                             : (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, false> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, false>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);
             kern<<<c->sm_count, PTB_TRACE_BLK_S, TraceSmem<PTB_TRACE_BLK_S>::fixed + TraceSmem<PTB_TRACE_BLK_S>::bvh(S.n), st>>>(S, io, tq, cur_tree, n_tree, ctr);
         } else if (mode == PTB_TREE_RESIDENT_QUANT) {
             // twice the size: resident as quantised 32-byte nodes
-            const bool s16 = c->s16_stack && c->tree_info.trav_depth >= 1 && c->tree_info.trav_depth <= PTB_S16_DEPTH && S.n <= 65536;
+            const bool s16 = ptb_s16_ok(c, S.n);
             auto kern = s16 ? (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true, false, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true, false, true>)
                             : (c->counting ? k_trace_tree<IO, true, PTB_TRACE_BLK_S, true, true> : k_trace_tree<IO, false, PTB_TRACE_BLK_S, true, true>);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin);

@@ -144,6 +144,31 @@ def test_traversal_structure_is_a_conservative_tree(gpu, name):
     assert np.all(ids[~visited] == -1) or not t['ploc']          # PLOC: entries it did not use are marked empty
 
 
+@pytest.mark.parametrize('name', ['cornell_boxes', 'cornell_monkey', 'matball', 'mega_small'])
+def test_traversal_stack_stays_within_the_tree_height(gpu, name):
+    """The resident tree kernels keep the whole stack in shared memory as 16 32-bit entries when the build says the tree is shallow
+    enough (wavefront.cu ptb_s16_ok: PLOC height - 1 <= 16): the deepest stack the production traversal reaches on incoherent rays
+    must stay below the height the build reports (one entry per level that has two internal children)."""
+    sc, o = load(gpu, name, SMALL[name])
+    t = gpu.tree
+    rng = np.random.default_rng(9)
+    m = 40000
+    verts = np.asarray(sc['vertices'], np.float32)[:, :3].reshape(-1, 3, 3)
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    org = rng.uniform(lo - 0.5, hi + 0.5, (m, 3))
+    d = rng.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, d], 1).astype(np.float32)
+    gpu.set_counting(True)
+    try:
+        gpu.reset_counters()
+        gpu.intersect(rays, None, _native.TRAVERSE_ORDERED)
+        got = gpu.counters()
+    finally:
+        gpu.set_counting(False)
+    assert got['rays'] == m and got['node_visits'] > 0
+    assert t.trav_depth >= 1 and got['max_stack'] <= (t.trav_depth - 1 if t.trav_ploc else t.trav_depth), (got['max_stack'], t.trav_depth)
+
+
 @pytest.mark.parametrize('name', ['cornell_monkey', 'mega_small'])
 def test_literal_traversal_work_counts_equal_the_oracle(gpu, name):
     """Integer parity of the work itself: under the literal policy (lbvh.py:313-347) the GPU pops, box-tests and triangle-tests
