@@ -822,3 +822,32 @@ def test_mlt_engine(gpu):
     valid = gpu.get_film()[..., 3] > 0
     ratio = mlt[valid].mean() / pt[valid].mean()
     assert 0.8 < ratio < 2.5, ratio
+
+
+def test_mlt_chain_shards_reproduce_the_population(gpu):
+    """chains are sharded contiguously across GPUs (dist.shard_chains) and chain c draws from the Philox stream
+    keyed (seed, c, iteration) wherever it runs.  On one GPU: the two halves of a population, run as shards (first, count), leave
+    exactly the per-chain state the whole population leaves, and their films add up to its film (weights exactly, colours up to the
+    order of the float atomics)."""
+    from ptina_b200.engine import MLTPathEngine
+    load(gpu, 'cornell_monkey', (64, 64), ref=False)
+    nch, half = 1 << 13, 1 << 12
+    MLTPathEngine._forget()
+    eng = MLTPathEngine(nchains=nch, seed=11)
+    try:
+        def run(first, count):
+            eng.chains = (first, count)
+            eng.reset()
+            worker.clear()
+            for _ in range(3):
+                eng.render(1)
+            return gpu.mlt_state(count), gpu.get_film().copy()
+        full, f_full = run(0, nch)
+        a, f_a = run(0, half)
+        b, f_b = run(half, nch - half)
+        for key in ('X_new', 'L_new', 'X_old', 'L_old'):
+            assert np.array_equal(full[key][:half], a[key]) and np.array_equal(full[key][half:], b[key]), key
+        assert f_full[..., 3].sum() == 3 * nch and np.array_equal(f_full[..., 3], f_a[..., 3] + f_b[..., 3])
+        assert np.allclose(f_full[..., :3], f_a[..., :3] + f_b[..., :3], rtol=1e-5, atol=1e-6)
+    finally:
+        MLTPathEngine._forget()
