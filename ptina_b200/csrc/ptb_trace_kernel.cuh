@@ -3,12 +3,12 @@
 // Production policy (PTB_TRAVERSE_ORDERED), two kernels per ray queue:
 //  k_trace_pre   : one ray per thread, uniform control flow.  Decodes the queue record, computes the per-ray constants of the
 //                  conservative slab test, tests the always-test list (every thread of a warp tests the same triangle: broadcast
-//                  loads), and tests the root box of the traversal tree.  A ray with nothing left to do (no box of the tree in
+//                  loads; identical boxes -- the two triangles of a wall quad -- are tested once), and tests the root box of the traversal tree.  A ray with nothing left to do (no box of the tree in
 //                  reach -- most rays of a room-like scene) is finished here; the others are appended, as self-contained 80-byte
 //                  records, to the tree queue.  Axis-parallel / non-finite rays, which the conservative test cannot handle, are
 //                  traced here with the exact routine (trace_ordered).
-//  k_trace_tree  : persistent warps, one ray per lane, traversal state in registers (stack: top entry in a register, the rest in
-//                  local memory).  A warp stages the records of the tree queue 16 at a time into a double-buffered shared-memory
+//  k_trace_tree  : persistent warps, one ray per lane, traversal state in registers (stack: first entries in shared memory, the rest in
+//                  local memory; shallow resident trees keep all of it in shared memory as 32-bit entries, S16).  A warp stages the records of the tree queue 16 at a time into a double-buffered shared-memory
 //                  tile with cp.async, so the DRAM latency of the next tile is covered by the traversal of the current one; a lane
 //                  that finishes its ray takes the next staged record.  Every iteration the warp votes for ONE kind of step -- a
 //                  node step (fetch a 64-B node, two conservative slab tests, push / descend) or a leaf step (gate test + triangle
