@@ -133,7 +133,7 @@ int ptb_create(int device, const ptb_caps* caps, ptb_ctx** out) {
     ptb_caps d{};
     if (caps) d = *caps;
     if (d.max_faces <= 0) d.max_faces = 1 << 21;          // things.py:13
-    if (d.max_faces > (1 << 24)) { ptb_set_error("max_faces %d above 2^24 (leaf slots are 24-bit fields of the ray queues)", d.max_faces); return 1; }
+    if (d.max_faces > (1 << 24)) { ptb_set_error("max_faces %d above 2^24 (leaf slots are 24-bit fields of the ray queues)", d.max_faces); delete c; return 1; }
     if (d.max_texels <= 0) d.max_texels = 1 << 22;        // things.py:14
     if (d.max_materials <= 0) d.max_materials = 64;
     if (d.max_textures <= 0) d.max_textures = 64;

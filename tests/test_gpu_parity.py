@@ -741,6 +741,9 @@ def test_edge_cases_and_errors(gpu):
     if o.validate_tree() < 0:
         assert gpu.tree.valid == 0 and gpu.tree.policy == _native.TRAVERSE_REFERENCE
     assert np.array_equal(gpu.trace_primary(65)['index'], o.primary(65)['index'])
+    # leaf slots travel in 24-bit fields of the ray queues (PTB_SLOT_MASK): a context sized for more faces is refused when it is created
+    with pytest.raises(_native.NativeError, match='2\\^24'):
+        _native.Context(max_faces=(1 << 24) + 1)
     load(gpu, 'cornell_boxes', (32, 32), ref=False)
 
 
